@@ -1,0 +1,239 @@
+// FP64 complex GEMM tile engine for sm_100a.
+//
+// Complex128 operands stay in numpy/torch interleaved (re,im) layout end to end.  Tiles are
+// staged global -> shared with a 4-deep cp.async (LDGSTS) ring; each lane pulls one complex
+// element per fragment with a single conflict-free LDS.128 and feeds the re/im halves to the
+// FP64 tensor pipe (mma.sync.m8n8k4.f64 == DMMA.8x8x4, the only FP64 MMA sm_100a has; tcgen05
+// has no f64 kind).  One complex MAC = 4 DMMA lanes-worth of FMAs (the "4M" form).
+//
+// CTA = 512 threads = 16 warps, warp tile 32(m) x 16(n) complex, CTA tile BM x BN with
+// (BM/32)*(BN/16) == 16, i.e. 128x64 or 64x128.  K step 8 complex per stage.
+//
+// Operand layouts: KCONTIG = [rows][K] row-major (K fastest), KSLOW = [K][rows] (rows fastest).
+#pragma once
+#include "common.cuh"
+
+namespace isdf {
+
+enum { MODE_CONJA = 0, MODE_CONJB = 1, MODE_AB = 2 };  // conj(a)*b, a*conj(b), a*b
+enum { EPI_STORE = 0, EPI_SUB_HERM = 1, EPI_HERK = 2, EPI_SQ_SYM = 3 };
+
+struct GemmParams {
+  const cplx* A; long lda; long strideA;
+  const cplx* B; long ldb; long strideB;
+  cplx* C;       long ldc; long strideC;
+  int M, N, K;
+  int nseg; long segA; long segB;  // accumulate over nseg K-segments (pointer += seg per segment)
+  double alpha;
+  const int* perm; long stridePerm;  // EPI_HERK: optional row/col scatter map per batch
+  const int* active;                 // optional per-batch flag; batch skipped when 0
+};
+
+constexpr int GEMM_BK = 8;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 512;
+
+template <int BM, int BN, bool A_KSLOW, bool B_KSLOW>
+struct GemmSmem {
+  static constexpr int LDA_S = A_KSLOW ? (BM + 2) : (GEMM_BK + 4);
+  static constexpr int LDB_S = B_KSLOW ? (BN + 2) : (GEMM_BK + 4);
+  static constexpr int A_TILE = A_KSLOW ? GEMM_BK * LDA_S : BM * LDA_S;
+  static constexpr int B_TILE = B_KSLOW ? GEMM_BK * LDB_S : BN * LDB_S;
+  static constexpr int BYTES = GEMM_STAGES * (A_TILE + B_TILE) * (int)sizeof(cplx);
+};
+
+template <int BM, int BN, bool A_KSLOW, bool B_KSLOW, int MODE, bool REAL_ONLY, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(GemmParams p) {
+  static_assert((BM / 32) * (BN / 16) == 16, "16 warps of 32x16");
+  constexpr int BK = GEMM_BK, STAGES = GEMM_STAGES;
+  using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW>;
+  constexpr int LDA_S = S::LDA_S, LDB_S = S::LDB_S, A_TILE = S::A_TILE, B_TILE = S::B_TILE;
+  constexpr int WARPS_N = BN / 16;
+  constexpr bool SYMM = (EPI == EPI_SUB_HERM || EPI == EPI_HERK || EPI == EPI_SQ_SYM);
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* sA = reinterpret_cast<cplx*>(smem_raw);
+  cplx* sB = sA + STAGES * A_TILE;
+
+  const int bz = blockIdx.z;
+  if (p.active != nullptr && p.active[bz] == 0) return;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (SYMM && n0 >= m0 + BM) return;  // tile strictly above the diagonal: produced by mirroring
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp / WARPS_N) * 32, wn0 = (warp % WARPS_N) * 16;
+  const int M = p.M, N = p.N, K = p.K;
+  const cplx* Abase = p.A + (long)bz * p.strideA;
+  const cplx* Bbase = p.B + (long)bz * p.strideB;
+  const int ktiles = (K + BK - 1) / BK;
+  const int nit = p.nseg * ktiles;
+
+  auto load_tiles = [&](int it, int slot) {
+    const int seg = it / ktiles;
+    const int k0 = (it - seg * ktiles) * BK;
+    const cplx* Ag = Abase + (long)seg * p.segA;
+    const cplx* Bg = Bbase + (long)seg * p.segB;
+    cplx* dA = sA + slot * A_TILE;
+    cplx* dB = sB + slot * B_TILE;
+    if (!A_KSLOW) {
+#pragma unroll
+      for (int c = tid; c < BM * BK; c += GEMM_THREADS) {
+        const int row = c / BK, kk = c % BK;
+        const bool v = (m0 + row < M) && (k0 + kk < K);
+        const cplx* src = v ? Ag + (long)(m0 + row) * p.lda + (k0 + kk) : Ag;
+        cp_async16(dA + row * LDA_S + kk, src, v);
+      }
+    } else {
+#pragma unroll
+      for (int c = tid; c < BK * BM; c += GEMM_THREADS) {
+        const int kk = c / BM, m = c % BM;
+        const bool v = (k0 + kk < K) && (m0 + m < M);
+        const cplx* src = v ? Ag + (long)(k0 + kk) * p.lda + (m0 + m) : Ag;
+        cp_async16(dA + kk * LDA_S + m, src, v);
+      }
+    }
+    if (!B_KSLOW) {
+#pragma unroll
+      for (int c = tid; c < BN * BK; c += GEMM_THREADS) {
+        const int row = c / BK, kk = c % BK;
+        const bool v = (n0 + row < N) && (k0 + kk < K);
+        const cplx* src = v ? Bg + (long)(n0 + row) * p.ldb + (k0 + kk) : Bg;
+        cp_async16(dB + row * LDB_S + kk, src, v);
+      }
+    } else {
+#pragma unroll
+      for (int c = tid; c < BK * BN; c += GEMM_THREADS) {
+        const int kk = c / BN, n = c % BN;
+        const bool v = (k0 + kk < K) && (n0 + n < N);
+        const cplx* src = v ? Bg + (long)(k0 + kk) * p.ldb + (n0 + n) : Bg;
+        cp_async16(dB + kk * LDB_S + n, src, v);
+      }
+    }
+  };
+
+  double acc_re[4][2][2];
+  double acc_im[REAL_ONLY ? 1 : 4][2][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      acc_re[mi][ni][0] = 0.0; acc_re[mi][ni][1] = 0.0;
+      if (!REAL_ONLY) { acc_im[mi][ni][0] = 0.0; acc_im[mi][ni][1] = 0.0; }
+    }
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nit) load_tiles(s, s);
+    cp_async_commit();
+  }
+
+  for (int it = 0; it < nit; ++it) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nx = it + STAGES - 1;
+      if (nx < nit) load_tiles(nx, nx % STAGES);
+      cp_async_commit();
+    }
+    const cplx* tA = sA + (it % STAGES) * A_TILE;
+    const cplx* tB = sB + (it % STAGES) * B_TILE;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ++ks) {
+      cplx a[4], b[2];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+        a[mi] = A_KSLOW ? tA[(ks * 4 + t) * LDA_S + wm0 + mi * 8 + g] : tA[(wm0 + mi * 8 + g) * LDA_S + ks * 4 + t];
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni)
+        b[ni] = B_KSLOW ? tB[(ks * 4 + t) * LDB_S + wn0 + ni * 8 + g] : tB[(wn0 + ni * 8 + g) * LDB_S + ks * 4 + t];
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        const double br = b[ni].x, bi = b[ni].y;
+        const double nbr = -br, nbi = -bi;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          const double ar = a[mi].x, ai = a[mi].y;
+          dmma884(acc_re[mi][ni][0], acc_re[mi][ni][1], ar, br);
+          dmma884(acc_re[mi][ni][0], acc_re[mi][ni][1], ai, (MODE == MODE_AB) ? nbi : bi);
+          if (!REAL_ONLY) {
+            if (MODE == MODE_CONJA) {         // im = ar*bi - ai*br
+              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, bi);
+              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, nbr);
+            } else if (MODE == MODE_CONJB) {  // im = ai*br - ar*bi
+              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, br);
+              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, nbi);
+            } else {                          // im = ar*bi + ai*br
+              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, bi);
+              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, br);
+            }
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  cplx* Cb = p.C + (long)bz * p.strideC;
+  const int* perm = (EPI == EPI_HERK && p.perm != nullptr) ? p.perm + (long)bz * p.stridePerm : nullptr;
+  const double alpha = p.alpha;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int r = m0 + wm0 + mi * 8 + g;
+    if (r >= M) continue;
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = n0 + wn0 + ni * 8 + 2 * t + e;
+        if (c >= N) continue;
+        const double vr = acc_re[mi][ni][e];
+        const double vi = REAL_ONLY ? 0.0 : acc_im[mi][ni][e];
+        if (EPI == EPI_STORE) {
+          Cb[(long)r * p.ldc + c] = make_double2(alpha * vr, alpha * vi);
+        } else if (EPI == EPI_SUB_HERM) {
+          if (r >= c) {
+            cplx* q = Cb + (long)r * p.ldc + c;
+            cplx o = *q;
+            *q = make_double2(o.x - vr, o.y - vi);
+            if (r > c) {
+              cplx* q2 = Cb + (long)c * p.ldc + r;
+              cplx o2 = *q2;
+              *q2 = make_double2(o2.x - vr, o2.y + vi);
+            }
+          }
+        } else if (EPI == EPI_HERK) {
+          if (r >= c) {
+            const int pr = perm ? perm[r] : r, pc = perm ? perm[c] : c;
+            Cb[(long)pr * p.ldc + pc] = make_double2(alpha * vr, alpha * vi);
+            if (r > c) Cb[(long)pc * p.ldc + pr] = make_double2(alpha * vr, -alpha * vi);
+          }
+        } else {  // EPI_SQ_SYM: out = alpha * re^2 (real, stored as complex with zero imaginary part)
+          if (r >= c) {
+            const double v = alpha * vr * vr;
+            Cb[(long)r * p.ldc + c] = make_double2(v, 0.0);
+            if (r > c) Cb[(long)c * p.ldc + r] = make_double2(v, 0.0);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int BM, int BN, bool A_KSLOW, bool B_KSLOW, int MODE, bool REAL_ONLY, int EPI>
+inline cudaError_t launch_gemm(const GemmParams& p, int batch, cudaStream_t st) {
+  using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW>;
+  auto kern = gemm_c128_kernel<BM, BN, A_KSLOW, B_KSLOW, MODE, REAL_ONLY, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
+  kern<<<grid, GEMM_THREADS, S::BYTES, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace isdf

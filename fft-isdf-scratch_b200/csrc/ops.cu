@@ -1,0 +1,162 @@
+// C-ABI entry points built on the DMMA GEMM engine, plus the handle and small data-movement kernels.
+#include "gemm_c128.cuh"
+
+namespace isdf {
+
+__global__ void conj_copy_kernel(const cplx* __restrict__ src, cplx* __restrict__ dst, long n) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const cplx v = src[i];
+    dst[i] = make_double2(v.x, -v.y);
+  }
+}
+
+// dst[z][i][:] = src[z][idx[z][i]][:]  (zeros when idx < 0)
+__global__ void gather_rows_kernel(const cplx* __restrict__ src, long lds, long strideS, const int* __restrict__ idx,
+                                   long strideI, int nrows, long ncols, cplx* __restrict__ dst, long ldd, long strideD) {
+  const int z = blockIdx.z;
+  const int i = blockIdx.y;
+  const int r = idx[(long)z * strideI + i];
+  const cplx* s = src + (long)z * strideS + (long)r * lds;
+  cplx* d = dst + (long)z * strideD + (long)i * ldd;
+  for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += (long)gridDim.x * blockDim.x)
+    d[c] = (r >= 0) ? s[c] : make_double2(0.0, 0.0);
+}
+
+}  // namespace isdf
+
+using namespace isdf;
+
+extern "C" int isdf_abi_version(void) { return 1; }
+
+extern "C" int isdf_create(int device, void** out) {
+  if (!out) return ISDF_EARG;
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  Handle* h = new Handle();
+  h->device = device;
+  h->err[0] = 0;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete h; return (int)e; }
+  if (prop.major != 10) {
+    // built for sm_100a only: refuse anything else loudly (no fallback path exists)
+    delete h;
+    return ISDF_ESIZE;
+  }
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = h;
+  return ISDF_OK;
+}
+
+extern "C" int isdf_fft_release_plans(void* hv);
+
+extern "C" int isdf_destroy(void* hv) {
+  if (!hv) return ISDF_OK;
+  isdf_fft_release_plans(hv);
+  delete (Handle*)hv;
+  return ISDF_OK;
+}
+
+extern "C" const char* isdf_last_error(void* hv) {
+  return hv ? ((Handle*)hv)->err : "null handle";
+}
+
+// x4c[g][h] = ( (sum_k Re(conj(x0[k,g,:]) . x0[k,h,:]))^2 / nk , 0 )      fftisdf.py:376-379
+extern "C" int isdf_select_gram(void* hv, const void* x0, int nk, int n0, int nao, void* x4c, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, x0 && x4c, "null pointer");
+  ISDF_CHECK_ARG(h, nk >= 1 && n0 >= 1 && nao >= 1, "shape");
+  GemmParams p;
+  p.A = (const cplx*)x0; p.lda = nao; p.strideA = 0;
+  p.B = (const cplx*)x0; p.ldb = nao; p.strideB = 0;
+  p.C = (cplx*)x4c; p.ldc = n0; p.strideC = 0;
+  p.M = n0; p.N = n0; p.K = nao;
+  p.nseg = nk; p.segA = (long)n0 * nao; p.segB = (long)n0 * nao;
+  p.alpha = 1.0 / (double)nk;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJA, true, EPI_SQ_SYM>(p, 1, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
+// c[z][i][j] = sum_l conj(a[z][i][l]) * b[z][j][l]       fftisdf.py:38 (x2_k), :76 (fx_k)
+extern "C" int isdf_gram_conja(void* hv, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                               void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, a && b && c, "null pointer");
+  ISDF_CHECK_ARG(h, m >= 0 && n >= 0 && k >= 0 && batch >= 0 && batch <= 65535, "shape");
+  ISDF_CHECK_ARG(h, (m + 127) / 128 <= 65535, "m too large for one launch");
+  GemmParams p;
+  p.A = (const cplx*)a; p.lda = lda; p.strideA = strideA;
+  p.B = (const cplx*)b; p.ldb = ldb; p.strideB = strideB;
+  p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
+  p.M = m; p.N = n; p.K = k;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJA, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
+// w[z][perm[i]][perm[j]] = alpha * sum_g b[z][i][g] conj(b[z][j][g])   (Hermitian; lower tiles + mirror)
+// fftisdf.py:121 in Parseval form: W_q = B B^H.
+extern "C" int isdf_herk_scatter(void* hv, const void* b, long ldb, long strideB, int n, int k, double alpha,
+                                 const int* perm, long stridePerm, void* w, long ldw, long strideW, int batch,
+                                 void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, b && w, "null pointer");
+  ISDF_CHECK_ARG(h, n >= 0 && k >= 0 && batch >= 0 && batch <= 65535, "shape");
+  GemmParams p;
+  p.A = (const cplx*)b; p.lda = ldb; p.strideA = strideB;
+  p.B = (const cplx*)b; p.ldb = ldb; p.strideB = strideB;
+  p.C = (cplx*)w; p.ldc = ldw; p.strideC = strideW;
+  p.M = n; p.N = n; p.K = k;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = alpha;
+  p.perm = perm; p.stridePerm = stridePerm; p.active = nullptr;
+  ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_HERK>(p, batch, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
+// c[z] = a[z] * b[z]  with a [m][k] row-major, b [k][n] row-major (plain complex GEMM, NN)
+extern "C" int isdf_gemm_nn(void* hv, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                            void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, a && b && c, "null pointer");
+  ISDF_CHECK_ARG(h, m >= 0 && n >= 0 && k >= 0 && batch >= 0 && batch <= 65535, "shape");
+  GemmParams p;
+  p.A = (const cplx*)a; p.lda = lda; p.strideA = strideA;
+  p.B = (const cplx*)b; p.ldb = ldb; p.strideB = strideB;
+  p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
+  p.M = m; p.N = n; p.K = k;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
+extern "C" int isdf_conj_copy(void* hv, const void* src, void* dst, long n, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, src && dst && n >= 0, "args");
+  if (n == 0) return ISDF_OK;
+  long blocks = (n + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  conj_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const cplx*)src, (cplx*)dst, n);
+  ISDF_LAUNCH_CHECK(h);
+  return ISDF_OK;
+}
+
+extern "C" int isdf_gather_rows(void* hv, const void* src, long lds, long strideS, const int* idx, long strideI,
+                                int nrows, long ncols, void* dst, long ldd, long strideD, int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, src && dst && idx, "null pointer");
+  ISDF_CHECK_ARG(h, nrows >= 0 && nrows <= 65535 && batch >= 0 && batch <= 65535 && ncols >= 0, "shape");
+  if (nrows == 0 || ncols == 0 || batch == 0) return ISDF_OK;
+  long bx = (ncols + 255) / 256;
+  if (bx > 64) bx = 64;
+  dim3 grid((unsigned)bx, nrows, batch);
+  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const cplx*)src, lds, strideS, idx, strideI, nrows, ncols,
+                                                             (cplx*)dst, ldd, strideD);
+  ISDF_LAUNCH_CHECK(h);
+  return ISDF_OK;
+}

@@ -1,0 +1,438 @@
+// Batched diagonal-pivoted Cholesky (LAPACK xPSTRF semantics) on Hermitian PSD matrices, plus the
+// helpers that turn its factor into the blocked triangular-sweep operators of the Theta fit.
+//
+// Serves two reference call sites:
+//   * point selection: pyscf.lib.scipy_helper.pivoted_cholesky(x4) -> scipy dpstrf
+//     (/root/reference/fftisdf.py:381-384).  x4 is real; it is carried as complex with zero
+//     imaginary parts, which makes every operation below bit-identical to the real recurrence.
+//   * the per-q least-squares fit scipy.linalg.lstsq(A_q, Y_q^T, "gelsy") (fftisdf.py:108): A_q is
+//     Hermitian PSD, so a rank-revealing Cholesky A_q[piv,piv] = U^H U replaces QRCP.
+//
+// Pivot rule (dpstrf): at step j take the FIRST maximum, in current position order, of the
+// residual diagonal a_ii - sum_{t in panel} |u_ti|^2; stop when it is <= n*eps*max_i a_ii (tol<0)
+// or <= tol.  Positions are tracked instead of physically swapping rows/columns.
+//
+// Structure: right-looking with panels of nb steps.  The panel kernel (one CTA per matrix, all
+// matrices of the batch concurrently) produces nb rows of U; the trailing update
+// A -= U_panel^H U_panel runs on the DMMA GEMM engine.
+#include <float.h>
+#include "gemm_c128.cuh"
+
+namespace isdf {
+
+constexpr int PC_THREADS = 1024;
+constexpr int PC_NCOL = 8;  // columns per thread -> n <= 8192
+constexpr int PC_NB_MAX = 64;
+
+struct PcholInfo {
+  int rank;
+  int done;
+  double dstop;
+  double next;  // value of the pivot that would come next (residual estimate, fftisdf.py:387)
+};
+
+__global__ void pchol_init_kernel(int* pos, PcholInfo* info, int* active, int n, int batch) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long)n * batch) pos[i] = (int)(i % n);
+  if (i < batch) {
+    info[i].rank = 0; info[i].done = 0; info[i].dstop = 0.0; info[i].next = 0.0;
+    active[i] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(PC_THREADS, 1)
+pchol_panel_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n, int j0, int nb, int max_steps,
+                   double tol, cplx* Uall, long ldu, long strideU, int* posall, PcholInfo* infoall, int* active) {
+  const int b = blockIdx.x;
+  PcholInfo* info = infoall + b;
+  if (info->done) return;
+  const cplx* A = Aall + (long)b * strideA;
+  cplx* U = Uall + (long)b * strideU;
+  int* pos = posall + (long)b * n;
+
+  __shared__ cplx bp[PC_NB_MAX];
+  __shared__ double red_v[32];
+  __shared__ int red_pos[32];
+  __shared__ int red_idx[32];
+  __shared__ double w_v;
+  __shared__ int w_pos, w_idx;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double aii[PC_NCOL], ssum[PC_NCOL];
+  int mypos[PC_NCOL];
+#pragma unroll
+  for (int c = 0; c < PC_NCOL; ++c) {
+    const int i = tid + c * PC_THREADS;
+    if (i < n) {
+      aii[c] = A[(long)i * lda + i].x;
+      ssum[c] = 0.0;
+      mypos[c] = pos[i];
+    } else {
+      aii[c] = 0.0; ssum[c] = 0.0; mypos[c] = -1;
+    }
+  }
+  double dstop = info->dstop;
+  int steps_done = 0;
+  bool stopped = false;
+
+  for (int t = 0; t <= nb; ++t) {
+    const int j = j0 + t;
+    if (t == nb && j < max_steps) break;  // panel complete; more panels follow
+    // ---- 1. first maximum of the residual diagonal over positions >= j
+    double bv = -DBL_MAX;
+    int bpos = 0x7fffffff, bidx = -1;
+#pragma unroll
+    for (int c = 0; c < PC_NCOL; ++c) {
+      if (mypos[c] >= j) {
+        const double d = aii[c] - ssum[c];
+        if (d > bv || (d == bv && mypos[c] < bpos)) { bv = d; bpos = mypos[c]; bidx = tid + c * PC_THREADS; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > bv || (ov == bv && op < bpos)) { bv = ov; bpos = op; bidx = oi; }
+    }
+    if (lane == 0) { red_v[warp] = bv; red_pos[warp] = bpos; red_idx[warp] = bidx; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = red_v[lane]; bpos = red_pos[lane]; bidx = red_idx[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ov > bv || (ov == bv && op < bpos)) { bv = ov; bpos = op; bidx = oi; }
+      }
+      if (lane == 0) { w_v = bv; w_pos = bpos; w_idx = bidx; }
+    }
+    __syncthreads();
+    const double dp = w_v;
+    const int p = w_idx, ppos = w_pos;
+    // ---- 2. stopping rule (dpstrf: ajj <= dstop or NaN; first pivot must be > 0)
+    if (j == 0) dstop = (tol < 0.0) ? (double)n * DBL_EPSILON * dp : tol;
+    if (p < 0 || j >= max_steps || !(dp > dstop) || !(dp > 0.0)) {
+      if (tid == 0) {
+        info->rank = j; info->done = 1; info->dstop = dstop;
+        info->next = (p < 0) ? 0.0 : dp;
+        active[b] = 0;
+      }
+      stopped = true;
+      break;
+    }
+    // ---- 3. position bookkeeping (swap positions j <-> ppos)
+#pragma unroll
+    for (int c = 0; c < PC_NCOL; ++c) {
+      const int i = tid + c * PC_THREADS;
+      if (i == p) mypos[c] = j;
+      else if (mypos[c] == j) mypos[c] = ppos;
+    }
+    // ---- 4. broadcast the pivot column's in-panel entries u_{t',p}
+    if (tid < t) bp[tid] = __ldcg(&U[(long)(j0 + tid) * ldu + p]);
+    __syncthreads();
+    // ---- 5. new row of U, residual update
+    const double rt = sqrt(dp);
+    const double inv = 1.0 / rt;
+    const cplx* Arow = A + (long)p * lda;
+#pragma unroll
+    for (int c = 0; c < PC_NCOL; ++c) {
+      const int i = tid + c * PC_THREADS;
+      if (i < n) {
+        cplx u;
+        if (i == p) {
+          u = make_double2(rt, 0.0);
+        } else if (mypos[c] > j) {
+          cplx v = Arow[i];
+          for (int tt = 0; tt < t; ++tt) {
+            const cplx ui = U[(long)(j0 + tt) * ldu + i];
+            const cplx bb = bp[tt];
+            // v -= conj(bb) * ui
+            v.x -= bb.x * ui.x + bb.y * ui.y;
+            v.y -= bb.x * ui.y - bb.y * ui.x;
+          }
+          u = make_double2(v.x * inv, v.y * inv);
+          ssum[c] += u.x * u.x + u.y * u.y;
+        } else {
+          u = make_double2(0.0, 0.0);
+        }
+        U[(long)j * ldu + i] = u;
+      }
+    }
+    steps_done = t + 1;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < PC_NCOL; ++c) {
+    const int i = tid + c * PC_THREADS;
+    if (i < n) pos[i] = mypos[c];
+  }
+  if (!stopped && tid == 0) { info->rank = j0 + steps_done; info->dstop = dstop; }
+}
+
+__global__ void pchol_finalize_kernel(const int* pos, const PcholInfo* info, int n, int batch, int* piv, int* rank,
+                                      double* next) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long)n * batch) {
+    const long b = i / n;
+    piv[b * n + pos[i]] = (int)(i % n);
+  }
+  if (i < batch) {
+    rank[i] = info[i].rank;
+    if (next) next[i] = info[i].next;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Triangular-sweep operator construction.
+// Up[a][b] = U[a][piv[b]] for a<=b<rank, identity on [rank, nP); Lp = Up^H.
+__global__ void build_up_lp_kernel(const cplx* Uall, long ldu, long strideU, const int* pivall, const int* rank, int n,
+                                   int nP, cplx* UpAll, cplx* LpAll) {
+  const int b = blockIdx.z;
+  const cplx* U = Uall + (long)b * strideU;
+  const int* piv = pivall + (long)b * n;
+  const int r = rank[b];
+  cplx* Up = UpAll + (long)b * nP * nP;
+  cplx* Lp = LpAll + (long)b * nP * nP;
+  __shared__ cplx tile[32][33];
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int yy = ty; yy < 32; yy += 8) {
+    const int a = a0 + yy, c = b0 + tx;
+    cplx v = make_double2(0.0, 0.0);
+    if (a < nP && c < nP) {
+      if (a < r && c < r && c >= a) v = U[(long)a * ldu + piv[c]];
+      else if (a == c && a >= r) v = make_double2(1.0, 0.0);
+      Up[(long)a * nP + c] = v;
+    }
+    tile[yy][tx] = v;
+  }
+  __syncthreads();
+  for (int yy = ty; yy < 32; yy += 8) {
+    const int c = b0 + yy, a = a0 + tx;  // Lp[c][a] = conj(Up[a][c])
+    if (a < nP && c < nP) {
+      const cplx v = tile[tx][yy];
+      Lp[(long)c * nP + a] = make_double2(v.x, -v.y);
+    }
+  }
+}
+
+// Invert the 64x64 upper-triangular diagonal blocks of Up; write Upinv into Ubwd's diagonal block
+// and its conjugate transpose into Lfwd's diagonal block.
+constexpr int TB = 64;
+__global__ void __launch_bounds__(TB) tri_inv_blocks_kernel(const cplx* UpAll, int nP, cplx* UbwdAll, cplx* LfwdAll) {
+  const int blk = blockIdx.x, b = blockIdx.y;
+  const cplx* Up = UpAll + (long)b * nP * nP + (long)blk * TB * nP + blk * TB;
+  cplx* Ub = UbwdAll + (long)b * nP * nP + (long)blk * TB * nP + blk * TB;
+  cplx* Lf = LfwdAll + (long)b * nP * nP + (long)blk * TB * nP + blk * TB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* sU = reinterpret_cast<cplx*>(smem_raw);  // [TB][TB+1]
+  cplx* sX = sU + TB * (TB + 1);                 // [TB][TB+1]  X[i][c]
+  const int c = threadIdx.x;
+  for (int i = 0; i < TB; ++i) sU[i * (TB + 1) + c] = Up[(long)i * nP + c];
+  __syncthreads();
+  // column c of the inverse: solve Up x = e_c by back substitution (x_i = 0 for i > c)
+  for (int i = TB - 1; i >= 0; --i) {
+    cplx acc = make_double2((i == c) ? 1.0 : 0.0, 0.0);
+    if (i <= c) {
+      for (int k = i + 1; k <= c; ++k) {
+        const cplx u = sU[i * (TB + 1) + k];
+        const cplx x = sX[k * (TB + 1) + c];
+        acc.x -= u.x * x.x - u.y * x.y;
+        acc.y -= u.x * x.y + u.y * x.x;
+      }
+      const cplx d = sU[i * (TB + 1) + i];
+      const double den = d.x * d.x + d.y * d.y;
+      const cplx q = make_double2((acc.x * d.x + acc.y * d.y) / den, (acc.y * d.x - acc.x * d.y) / den);
+      sX[i * (TB + 1) + c] = q;
+    } else {
+      sX[i * (TB + 1) + c] = make_double2(0.0, 0.0);
+    }
+  }
+  __syncthreads();
+  for (int i = 0; i < TB; ++i) {
+    const cplx x = sX[i * (TB + 1) + c];
+    Ub[(long)i * nP + c] = x;                       // Upinv[i][c]
+    const cplx y = sX[c * (TB + 1) + i];            // Upinv[c][i]
+    Lf[(long)i * nP + c] = make_double2(y.x, -y.y); // Linv[i][c] = conj(Upinv[c][i])
+  }
+}
+
+// Off-diagonal blocks: Ubwd[a][cb] = -Upinv_aa * Up[a][cb] (cb > a), Lfwd[a][cb] = -Linv_aa * Lp[a][cb] (cb < a).
+__global__ void __launch_bounds__(256) apply_diag_inv_kernel(const cplx* UpAll, const cplx* LpAll, int nP, cplx* UbwdAll,
+                                                             cplx* LfwdAll) {
+  const int nblk = nP / TB;
+  const int a = blockIdx.y, cb = blockIdx.x, b = blockIdx.z;
+  if (cb == a) return;
+  const bool upper = cb > a;
+  const cplx* Src = (upper ? UpAll : LpAll) + (long)b * nP * nP + (long)a * TB * nP + cb * TB;
+  cplx* Dst = (upper ? UbwdAll : LfwdAll) + (long)b * nP * nP + (long)a * TB * nP + cb * TB;
+  const cplx* Inv = (upper ? UbwdAll : LfwdAll) + (long)b * nP * nP + (long)a * TB * nP + a * TB;
+  (void)nblk;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* sI = reinterpret_cast<cplx*>(smem_raw);  // [TB][TB+1]
+  cplx* sS = sI + TB * (TB + 1);                 // [TB][TB+1]
+  for (int w = threadIdx.x; w < TB * TB; w += 256) {
+    const int i = w / TB, j = w % TB;
+    sI[i * (TB + 1) + j] = Inv[(long)i * nP + j];
+    sS[i * (TB + 1) + j] = Src[(long)i * nP + j];
+  }
+  __syncthreads();
+  // 256 threads, each a 4x4 patch: rows ty*4.., cols tx*4..  (tx fastest)
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  cplx acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_double2(0.0, 0.0);
+  for (int k = 0; k < TB; ++k) {
+    cplx av[4], bv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) av[i] = sI[(ty * 4 + i) * (TB + 1) + k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bv[j] = sS[k * (TB + 1) + tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cfma(acc[i][j], av[i], bv[j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      Dst[(long)(ty * 4 + i) * nP + tx + 16 * j] = make_double2(-acc[i][j].x, -acc[i][j].y);
+}
+
+}  // namespace isdf
+
+using namespace isdf;
+
+extern "C" int isdf_pchol_workspace_bytes(int n, int batch, size_t* bytes) {
+  if (!bytes || n <= 0 || batch <= 0) return ISDF_EARG;
+  size_t b = (size_t)n * batch * sizeof(int);            // pos
+  b = (b + 255) / 256 * 256;
+  b += (size_t)batch * sizeof(PcholInfo);
+  b = (b + 255) / 256 * 256;
+  b += (size_t)batch * sizeof(int);                      // active
+  *bytes = (b + 255) / 256 * 256;
+  return ISDF_OK;
+}
+
+// a: [batch][n][n] c128 Hermitian PSD, overwritten by its trailing Schur complements.
+// u: [batch][ldu_rows][n] c128, rows j < rank hold row j of the factor A = U^H U in ORIGINAL column
+//    order (column piv[j] carries the pivot); must be zero-initialised by the caller? -> zeroed here.
+extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
+                          int ldu_rows, int* piv, int* rank, double* next_pivot, void* workspace, void* stream) {
+  Handle* h = (Handle*)hv;
+  cudaStream_t st = (cudaStream_t)stream;
+  ISDF_CHECK_ARG(h, a && u && piv && rank && workspace, "null pointer");
+  ISDF_CHECK_ARG(h, n >= 1 && n <= PC_THREADS * PC_NCOL, "n must be in [1, 8192]");
+  ISDF_CHECK_ARG(h, batch >= 1, "batch");
+  ISDF_CHECK_ARG(h, max_steps >= 0 && max_steps <= n && max_steps <= ldu_rows, "max_steps");
+  if (nb <= 0) nb = 32;
+  ISDF_CHECK_ARG(h, nb <= PC_NB_MAX, "nb <= 64");
+  char* w = (char*)workspace;
+  int* pos = (int*)w;
+  size_t off = ((size_t)n * batch * sizeof(int) + 255) / 256 * 256;
+  PcholInfo* info = (PcholInfo*)(w + off);
+  off += ((size_t)batch * sizeof(PcholInfo) + 255) / 256 * 256;
+  int* active = (int*)(w + off);
+
+  ISDF_CUDA(h, cudaMemsetAsync(u, 0, (size_t)batch * ldu_rows * n * sizeof(cplx), st));
+  {
+    const long tot = (long)n * batch;
+    pchol_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pos, info, active, n, batch);
+    ISDF_LAUNCH_CHECK(h);
+  }
+  const long strideA = (long)n * n, strideU = (long)ldu_rows * n;
+  // The panel that reaches max_steps also evaluates the would-be next pivot and sets the stop flag.
+  for (int j0 = 0; j0 == 0 || j0 < max_steps; j0 += nb) {
+    pchol_panel_kernel<<<batch, PC_THREADS, 0, st>>>((const cplx*)a, n, strideA, n, j0, nb, max_steps, tol, (cplx*)u, n,
+                                                     strideU, pos, info, active);
+    ISDF_LAUNCH_CHECK(h);
+    if (j0 + nb < max_steps) {
+      // trailing update A -= U_p^H U_p (only needed while further pivot rows will be read)
+      GemmParams p;
+      p.A = (const cplx*)u + (long)j0 * n; p.lda = n; p.strideA = strideU;
+      p.B = p.A; p.ldb = n; p.strideB = strideU;
+      p.C = (cplx*)a; p.ldc = n; p.strideC = strideA;
+      p.M = n; p.N = n; p.K = nb;
+      p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+      p.perm = nullptr; p.stridePerm = 0; p.active = active;
+      ISDF_CUDA(h, (launch_gemm<128, 64, true, true, MODE_CONJA, false, EPI_SUB_HERM>(p, batch, st)));
+    }
+  }
+  {
+    const long tot = (long)n * batch;
+    pchol_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pos, info, n, batch, piv, rank, next_pivot);
+    ISDF_LAUNCH_CHECK(h);
+  }
+  return ISDF_OK;
+}
+
+// From the pivoted factor build the block operators of the two triangular sweeps (block size 64):
+//   forward  T_a <- sum_{b<=a} Lfwd[a][b] T_b,   backward T_a <- sum_{b>=a} Ubwd[a][b] T_b.
+// work: 2 * batch * nP * nP c128 (Up, Lp).  lfwd, ubwd: batch * nP * nP c128 each.
+extern "C" int isdf_trsm_prepare(void* hv, const void* u, int ldu_rows, const int* piv, const int* rank, int n, int nP,
+                                 int batch, void* lfwd, void* ubwd, void* work, void* stream) {
+  Handle* h = (Handle*)hv;
+  cudaStream_t st = (cudaStream_t)stream;
+  ISDF_CHECK_ARG(h, u && piv && rank && lfwd && ubwd && work, "null pointer");
+  ISDF_CHECK_ARG(h, nP % TB == 0 && nP >= n && n >= 1, "nP must be a multiple of 64 and >= n");
+  ISDF_CHECK_ARG(h, batch >= 1 && batch <= 65535, "batch");
+  cplx* Up = (cplx*)work;
+  cplx* Lp = Up + (long)batch * nP * nP;
+  {
+    dim3 grid((nP + 31) / 32, (nP + 31) / 32, batch), block(32, 8);
+    build_up_lp_kernel<<<grid, block, 0, st>>>((const cplx*)u, n, (long)ldu_rows * n, piv, rank, n, nP, Up, Lp);
+    ISDF_LAUNCH_CHECK(h);
+  }
+  const int nblk = nP / TB;
+  const size_t sm = 2 * TB * (TB + 1) * sizeof(cplx);
+  ISDF_CUDA(h, cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  ISDF_CUDA(h, cudaFuncSetAttribute(apply_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  {
+    dim3 grid(nblk, batch);
+    tri_inv_blocks_kernel<<<grid, TB, sm, st>>>(Up, nP, (cplx*)ubwd, (cplx*)lfwd);
+    ISDF_LAUNCH_CHECK(h);
+  }
+  if (nblk > 1) {
+    dim3 grid(nblk, nblk, batch);
+    apply_diag_inv_kernel<<<grid, 256, sm, st>>>(Up, Lp, nP, (cplx*)ubwd, (cplx*)lfwd);
+    ISDF_LAUNCH_CHECK(h);
+  }
+  return ISDF_OK;
+}
+
+// In-place blocked substitution  T <- U^{-1} U^{-H} T  on T[batch][nP][ng] (row-major, ng contiguous).
+extern "C" int isdf_trsm_sweeps(void* hv, const void* lfwd, const void* ubwd, void* t, int nP, long ng, long ldt,
+                                int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  cudaStream_t st = (cudaStream_t)stream;
+  ISDF_CHECK_ARG(h, lfwd && ubwd && t, "null pointer");
+  ISDF_CHECK_ARG(h, nP % TB == 0 && ng >= 1 && ng < (1L << 31) && ldt >= ng, "shape");
+  const int nblk = nP / TB;
+  GemmParams p;
+  p.lda = nP; p.strideA = (long)nP * nP;
+  p.ldb = ldt; p.strideB = (long)nP * ldt;
+  p.ldc = ldt; p.strideC = (long)nP * ldt;
+  p.M = TB; p.N = (int)ng;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  for (int a = 0; a < nblk; ++a) {  // forward: rows 0..a
+    p.A = (const cplx*)lfwd + (long)a * TB * nP;
+    p.B = (const cplx*)t;
+    p.C = (cplx*)t + (long)a * TB * ldt;
+    p.K = (a + 1) * TB;
+    ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st)));
+  }
+  for (int a = nblk - 1; a >= 0; --a) {  // backward: rows a..end
+    p.A = (const cplx*)ubwd + (long)a * TB * nP + (long)a * TB;
+    p.B = (const cplx*)t + (long)a * TB * ldt;
+    p.C = (cplx*)t + (long)a * TB * ldt;
+    p.K = nP - a * TB;
+    ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st)));
+  }
+  return ISDF_OK;
+}

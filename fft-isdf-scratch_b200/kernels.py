@@ -1,0 +1,176 @@
+"""Thin torch-tensor wrappers around the C-ABI entry points of libisdf_b200.so.
+
+torch is used for device memory and streams only; every arithmetic operation on the hot path is
+one of the hand-written sm_100a kernels behind `_cabi.Handle`.  All tensors are complex128 /
+float64 / int32, contiguous, on the handle's device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._cabi import Handle
+
+KT_NMAX = 8
+TB = 64  # triangular-sweep block size (csrc/pchol.cu)
+
+c128 = torch.complex128
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype):
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.dtype, t.is_contiguous())
+
+
+class IsdfOps:
+    def __init__(self, device=0):
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.handle = Handle(device)
+        self.lib = self.handle.lib
+        self.h = self.handle.h
+        self.launches = 0  # kernels launched through this object (bench.py's gpu_launches)
+
+    # ---- K1: selection Gram  (fftisdf.py:376-379) --------------------------------------
+    def select_gram(self, x0):
+        _chk(x0, c128)
+        nk, n0, nao = x0.shape
+        x4c = torch.empty((n0, n0), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_select_gram(self.h, _ptr(x0), nk, n0, nao, _ptr(x4c), _stream()),
+                          "isdf_select_gram")
+        self.launches += 1
+        return x4c
+
+    # ---- K2/K5a: batched pivoted Cholesky ------------------------------------------------
+    def pchol(self, a, max_steps, tol=-1.0, nb=32):
+        """a: [batch, n, n] Hermitian PSD (destroyed).  Returns (u, piv, rank, next_pivot)."""
+        _chk(a, c128)
+        batch, n, _ = a.shape
+        ldu = max(1, max_steps)
+        u = torch.empty((batch, ldu, n), dtype=c128, device=self.device)
+        piv = torch.empty((batch, n), dtype=torch.int32, device=self.device)
+        rank = torch.empty((batch,), dtype=torch.int32, device=self.device)
+        nxt = torch.empty((batch,), dtype=torch.float64, device=self.device)
+        nbytes = C.c_size_t()
+        self.lib.isdf_pchol_workspace_bytes(n, batch, C.byref(nbytes))
+        work = torch.empty((nbytes.value,), dtype=torch.uint8, device=self.device)
+        self.handle.check(self.lib.isdf_pchol(self.h, _ptr(a), n, batch, int(max_steps), float(tol), int(nb), _ptr(u),
+                                              ldu, _ptr(piv), _ptr(rank), _ptr(nxt), _ptr(work), _stream()),
+                          "isdf_pchol")
+        npan = max(1, -(-max_steps // nb))
+        self.launches += 3 + 2 * npan
+        return u, piv, rank, nxt
+
+    # ---- batched conj(A) B^T  (fftisdf.py:38, :76) -----------------------------------------
+    def gram_conja(self, a, b, out=None):
+        _chk(a, c128), _chk(b, c128)
+        batch, m, k = a.shape
+        _, n, _ = b.shape
+        if out is None:
+            out = torch.empty((batch, m, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gram_conja(self.h, _ptr(a), k, m * k, _ptr(b), k, n * k, _ptr(out), n, m * n,
+                                                   m, n, k, batch, _stream()), "isdf_gram_conja")
+        self.launches += 1
+        return out
+
+    def gemm_nn(self, a, b):
+        _chk(a, c128), _chk(b, c128)
+        batch, m, k = a.shape
+        _, _, n = b.shape
+        out = torch.empty((batch, m, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gemm_nn(self.h, _ptr(a), k, m * k, _ptr(b), n, k * n, _ptr(out), n, m * n,
+                                                m, n, k, batch, _stream()), "isdf_gemm_nn")
+        self.launches += 1
+        return out
+
+    # ---- k<->R transform, square, k<->R transform ------------------------------------------
+    def pack_uaxes(self, kmesh):
+        from .pbc_tools import get_phase_axes
+        u = np.zeros((3, KT_NMAX, KT_NMAX), dtype=np.complex128)
+        for a, m in enumerate(get_phase_axes(kmesh)):
+            assert m.shape[0] <= KT_NMAX, "k-mesh axis > 8 not supported by the k-transform kernel"
+            u[a, : m.shape[0], : m.shape[1]] = m
+        return torch.from_numpy(u).to(self.device)
+
+    def ktransform_square(self, vin, in_sk, in_sg, out, out_sq, out_sg, out_si, out_g0, ng, ni, kmesh, uaxes,
+                          conj2, out_g_fast, qslot=None, rowmap=None, rowmap_sq=0, diag=None):
+        km = (C.c_int * 3)(*[int(x) for x in kmesh])
+        self.handle.check(self.lib.isdf_ktransform_square(
+            self.h, _ptr(vin), in_sk, in_sg, _ptr(out), out_sq, out_sg, out_si, out_g0, ng, ni, km, _ptr(uaxes),
+            int(conj2), int(out_g_fast), _ptr(qslot), _ptr(rowmap), rowmap_sq, _ptr(diag), _stream()),
+            "isdf_ktransform_square")
+        self.launches += 1
+
+    # ---- K5: triangular sweeps ----------------------------------------------------------------
+    def trsm_prepare(self, u, piv, rank, nP):
+        batch, ldu, n = u.shape
+        lfwd = torch.zeros((batch, nP, nP), dtype=c128, device=self.device)
+        ubwd = torch.zeros((batch, nP, nP), dtype=c128, device=self.device)
+        work = torch.empty((2, batch, nP, nP), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_trsm_prepare(self.h, _ptr(u), ldu, _ptr(piv), _ptr(rank), n, nP, batch,
+                                                     _ptr(lfwd), _ptr(ubwd), _ptr(work), _stream()),
+                          "isdf_trsm_prepare")
+        self.launches += 3
+        return lfwd, ubwd
+
+    def trsm_sweeps(self, lfwd, ubwd, t):
+        _chk(t, c128)
+        batch, nP, ng = t.shape
+        self.handle.check(self.lib.isdf_trsm_sweeps(self.h, _ptr(lfwd), _ptr(ubwd), _ptr(t), nP, ng, ng, batch,
+                                                    _stream()), "isdf_trsm_sweeps")
+        self.launches += 2 * (nP // TB)
+
+    # ---- K6: batched 3-D FFT with fused phase / weight ----------------------------------------
+    def fft3d(self, data, mesh, pre=None, post=None, group_vecs=0):
+        _chk(data, c128)
+        nvec = data.numel() // int(np.prod(mesh))
+        m = (C.c_int * 3)(*[int(x) for x in mesh])
+        self.handle.check(self.lib.isdf_fft3d_batched(self.h, _ptr(data), nvec, m, _ptr(pre), _ptr(post),
+                                                      int(group_vecs), _stream()), "isdf_fft3d_batched")
+        ng = int(np.prod(mesh))
+        gv = group_vecs if group_vecs > 0 else max(1, int(48 * 1024 * 1024 / (ng * 16)))
+        self.launches += 3 * (-(-nvec // gv))
+
+    # ---- K7: W = alpha * B B^H, scattered through perm -------------------------------------------
+    def herk(self, b, alpha=1.0, perm=None, out=None):
+        _chk(b, c128)
+        batch, n, k = b.shape
+        if out is None:
+            out = torch.empty((batch, n, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_herk_scatter(self.h, _ptr(b), k, n * k, n, k, float(alpha), _ptr(perm),
+                                                     (perm.shape[-1] if perm is not None else 0), _ptr(out), n, n * n,
+                                                     batch, _stream()), "isdf_herk_scatter")
+        self.launches += 1
+        return out
+
+    def herk_strided(self, b_ptr_tensor, ldb, strideB, n, k, alpha, perm, stride_perm, out, batch):
+        self.handle.check(self.lib.isdf_herk_scatter(self.h, _ptr(b_ptr_tensor), ldb, strideB, n, k, float(alpha),
+                                                     _ptr(perm), stride_perm, _ptr(out), n, n * n, batch, _stream()),
+                          "isdf_herk_scatter")
+        self.launches += 1
+
+    def conj_copy(self, src, dst):
+        self.handle.check(self.lib.isdf_conj_copy(self.h, _ptr(src), _ptr(dst), src.numel(), _stream()),
+                          "isdf_conj_copy")
+        self.launches += 1
+
+    def gather_rows(self, src, idx, ncols=None, out=None):
+        """src [batch, R, ncols], idx [batch, nrows] int32 -> out [batch, nrows, ncols] (zeros where idx<0)."""
+        _chk(src, c128)
+        batch, R, nc = src.shape
+        nrows = idx.shape[-1]
+        if out is None:
+            out = torch.empty((batch, nrows, nc), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gather_rows(self.h, _ptr(src), nc, R * nc, _ptr(idx), nrows, nrows, nc,
+                                                    _ptr(out), nc, nrows * nc, batch, _stream()), "isdf_gather_rows")
+        self.launches += 1
+        return out

@@ -1,0 +1,230 @@
+"""Kernel-level parity: every C-ABI entry point against numpy/scipy on the same seeded inputs.
+Tolerances are stated per test (FP64; relative to the largest reference entry)."""
+import numpy as np
+import pytest
+import scipy.linalg
+import torch
+
+from oracle import pbc_helpers as H
+from oracle import isdf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def crand(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("shape", [(3, 150, 70, 37), (1, 128, 64, 8), (2, 5, 3, 1), (1, 257, 129, 26)])
+def test_gram_conja(ops, shape):
+    batch, m, n, k = shape
+    rng = np.random.default_rng(1)
+    a, b = crand(rng, batch, m, k), crand(rng, batch, n, k)
+    c = ops.gram_conja(dev(a), dev(b)).cpu().numpy()
+    ref = np.einsum("zik,zjk->zij", a.conj(), b)
+    assert relerr(c, ref) < 1e-13
+
+
+def test_select_gram(ops):
+    rng = np.random.default_rng(2)
+    nk, n0, nao = 3, 203, 7
+    x0 = crand(rng, nk, n0, nao)
+    x4 = ops.select_gram(dev(x0)).cpu().numpy()
+    x2 = sum((x0[q].conj() @ x0[q].T).real for q in range(nk))
+    ref = x2 * x2 / nk
+    assert relerr(x4.real, ref) < 1e-13
+    assert np.abs(x4.imag).max() == 0.0
+    assert np.array_equal(x4.real, x4.real.T)  # exactly symmetric (mirrored tiles)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 300, 130), (1, 64, 128, 64), (3, 40, 77, 19)])
+def test_gemm_nn(ops, shape):
+    batch, m, n, k = shape
+    rng = np.random.default_rng(3)
+    a, b = crand(rng, batch, m, k), crand(rng, batch, k, n)
+    c = ops.gemm_nn(dev(a), dev(b)).cpu().numpy()
+    assert relerr(c, a @ b) < 1e-13
+
+
+def test_herk_scatter(ops):
+    rng = np.random.default_rng(4)
+    batch, n, k = 2, 150, 1003
+    b = crand(rng, batch, n, k)
+    perm = np.stack([rng.permutation(n) for _ in range(batch)]).astype(np.int32)
+    w = ops.herk(dev(b), alpha=0.5, perm=dev(perm)).cpu().numpy()
+    for z in range(batch):
+        ref = np.zeros((n, n), complex)
+        ref[np.ix_(perm[z], perm[z])] = 0.5 * b[z] @ b[z].conj().T
+        assert relerr(w[z], ref) < 1e-13
+        assert np.array_equal(w[z], w[z].conj().T)  # exactly Hermitian
+
+
+def _psd(rng, n, r, complex_=True):
+    b = crand(rng, n, r) if complex_ else rng.standard_normal((n, r)) + 0j
+    return b @ b.conj().T
+
+
+@pytest.mark.parametrize("n,r,nb", [(200, 200, 32), (130, 40, 16), (300, 300, 64), (65, 65, 7)])
+def test_pchol_complex(ops, n, r, nb):
+    rng = np.random.default_rng(5)
+    a = np.stack([_psd(rng, n, r), _psd(rng, n, r)])
+    u, piv, rank, nxt = ops.pchol(dev(a.copy()), max_steps=n, tol=-1.0, nb=nb)
+    u, piv, rank = u.cpu().numpy(), piv.cpu().numpy(), rank.cpu().numpy()
+    for z in range(2):
+        rk = int(rank[z])
+        assert (rk == n) if r == n else (r <= rk <= r + 2)
+        assert sorted(piv[z].tolist()) == list(range(n))
+        rec = u[z, :rk].conj().T @ u[z, :rk]
+        assert relerr(rec, a[z]) < 1e-11
+        up = u[z, :rk][:, piv[z][:rk]]
+        assert np.abs(np.tril(up, -1)).max() == 0.0  # upper triangular in pivot order
+        d = np.diag(up).real
+        assert np.all(d[:-1] >= d[1:] * (1 - 1e-12))  # non-increasing pivots
+
+
+def test_pchol_matches_dpstrf_real(ops):
+    """Real symmetric input carried as complex: pivots identical to LAPACK dpstrf (tie-free input)."""
+    rng = np.random.default_rng(6)
+    n = 257
+    x = rng.standard_normal((n, 60))
+    x2 = x @ x.T
+    x4 = x2 * x2
+    _, piv_ref, rank_ref = H.pivoted_cholesky(x4.copy())
+    nsteps = 120
+    u, piv, rank, nxt = ops.pchol(dev(x4[None].astype(complex)), max_steps=nsteps, tol=-1.0, nb=32)
+    piv = piv.cpu().numpy()[0]
+    assert int(rank.cpu()[0]) == nsteps
+    assert np.array_equal(piv[:nsteps], piv_ref[:nsteps])
+    p2, steps, nx = H.pivoted_cholesky_steps(x4, nsteps)
+    assert np.array_equal(piv[:nsteps], p2)
+    assert abs(float(nxt.cpu()[0]) - nx) <= 1e-9 * abs(nx)
+
+
+def test_pchol_early_stop_and_zero_steps(ops):
+    rng = np.random.default_rng(7)
+    a = _psd(rng, 90, 90)[None]
+    u, piv, rank, nxt = ops.pchol(dev(a.copy()), max_steps=0)
+    assert int(rank.cpu()[0]) == 0
+    assert abs(float(nxt.cpu()[0]) - np.diag(a[0]).real.max()) < 1e-12 * np.diag(a[0]).real.max()
+    u, piv, rank, nxt = ops.pchol(dev(a.copy()), max_steps=90, tol=1e300)
+    assert int(rank.cpu()[0]) == 0
+
+
+@pytest.mark.parametrize("n,ng", [(100, 517), (64, 128), (200, 1000)])
+def test_trsm_solve(ops, n, ng):
+    rng = np.random.default_rng(8)
+    batch = 2
+    a = np.stack([_psd(rng, n, n + 20) + 0.1 * np.eye(n) for _ in range(batch)])
+    y = crand(rng, batch, n, ng)
+    u, piv, rank, _ = ops.pchol(dev(a.copy()), max_steps=n)
+    nP = -(-n // 64) * 64
+    lfwd, ubwd = ops.trsm_prepare(u, piv, rank, nP)
+    pivh = piv.cpu().numpy()
+    t = np.zeros((batch, nP, ng), complex)
+    for z in range(batch):
+        t[z, :n] = y[z][pivh[z]]
+    td = dev(t)
+    ops.trsm_sweeps(lfwd, ubwd, td)
+    sol = td.cpu().numpy()
+    for z in range(batch):
+        ref = np.linalg.solve(a[z], y[z])
+        got = np.zeros_like(ref)
+        got[pivh[z]] = sol[z, :n]
+        assert relerr(got, ref) < 1e-10
+        assert np.abs(sol[z, n:]).max() == 0.0
+
+
+@pytest.mark.parametrize("kmesh", [[1, 1, 1], [2, 2, 2], [3, 2, 1], [4, 4, 4], [1, 5, 3]])
+def test_ktransform_metric_and_rhs(ops, kmesh):
+    rng = np.random.default_rng(9)
+    nk = int(np.prod(kmesh))
+    a = np.eye(3) * 6.0 + 0.3 * rng.standard_normal((3, 3))
+    kpts = H.get_kpts(a, kmesh)
+    phase = H.get_phase(a, kpts, kmesh)
+    nip, blk = 21, 37
+    # time-reversal symmetric real-space tables -> k-space (so that phase @ v is real)
+    vs = rng.standard_normal((nk, blk * nip))
+    vk = (phase.conj().T @ vs).reshape(nk, blk, nip)
+    uax = ops.pack_uaxes(kmesh)
+    diag = torch.zeros(2, dtype=torch.float64, device="cuda")
+    # rhs form: out[q][i][g] (transposed), phase.T second transform
+    out = torch.zeros((nk, nip, 50), dtype=torch.complex128, device="cuda")
+    ops.ktransform_square(dev(vk), blk * nip, nip, out, nip * 50, 1, 50, 5, blk, nip, kmesh, uax, 0, 1, diag=diag)
+    ys = (phase @ vk.reshape(nk, -1))
+    ref = (phase.T @ (ys * ys)).reshape(nk, blk, nip)
+    got = out.cpu().numpy()[:, :, 5:5 + blk].transpose(0, 2, 1)
+    assert relerr(got, ref) < 1e-13
+    d = diag.cpu().numpy()
+    assert d[0] < 1e-12 and abs(d[1] - np.abs(ys.real).max()) < 1e-12
+    # metric form: out[q][g][i], phase^H second transform
+    out2 = torch.zeros((nk, blk, nip), dtype=torch.complex128, device="cuda")
+    ops.ktransform_square(dev(vk), blk * nip, nip, out2, blk * nip, nip, 1, 0, blk, nip, kmesh, uax, 1, 0)
+    ref2 = (phase.conj().T @ (ys * ys)).reshape(nk, blk, nip)
+    assert relerr(out2.cpu().numpy(), ref2) < 1e-13
+
+
+def test_ktransform_qslot_rowmap(ops):
+    rng = np.random.default_rng(10)
+    kmesh = [2, 2, 1]
+    nk = 4
+    a = np.eye(3) * 5.0
+    phase = H.get_phase(a, H.get_kpts(a, kmesh), kmesh)
+    nip, blk = 10, 9
+    vs = rng.standard_normal((nk, blk * nip))
+    vk = (phase.conj().T @ vs).reshape(nk, blk, nip)
+    qslot = np.array([0, -1, 1, -1], dtype=np.int32)
+    rowmap = np.stack([rng.permutation(nip), rng.permutation(nip)]).astype(np.int32)
+    rowmap[0, 3] = -1
+    out = torch.zeros((2, nip, blk), dtype=torch.complex128, device="cuda")
+    ops.ktransform_square(dev(vk), blk * nip, nip, out, nip * blk, 1, blk, 0, blk, nip, kmesh, ops.pack_uaxes(kmesh),
+                          0, 1, qslot=dev(qslot), rowmap=dev(rowmap), rowmap_sq=nip)
+    ys = phase @ vk.reshape(nk, -1)
+    full = (phase.T @ (ys * ys)).reshape(nk, blk, nip)
+    got = out.cpu().numpy()
+    for slot, q in enumerate([0, 2]):
+        ref = np.zeros((nip, blk), complex)
+        for i in range(nip):
+            if rowmap[slot, i] >= 0:
+                ref[rowmap[slot, i]] = full[q][:, i]
+        assert relerr(got[slot], ref) < 1e-13
+
+
+@pytest.mark.parametrize("mesh", [[9, 10, 12], [15, 15, 15], [37, 5, 4], [32, 32, 32], [1, 1, 7], [33, 31, 36]])
+def test_fft3d(ops, mesh):
+    rng = np.random.default_rng(11)
+    ng = int(np.prod(mesh))
+    nvec = 5
+    x = crand(rng, nvec, ng)
+    pre = np.exp(1j * rng.uniform(0, 6.28, ng))
+    post = rng.uniform(0.1, 2.0, ng)
+    d = dev(x.copy())
+    ops.fft3d(d, mesh, pre=dev(pre), post=dev(post), group_vecs=2)
+    ref = np.fft.fftn((x * pre).reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng) * post
+    assert relerr(d.cpu().numpy(), ref) < 1e-13
+    d = dev(x.copy())
+    ops.fft3d(d, mesh)
+    ref = np.fft.fftn(x.reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng)
+    assert relerr(d.cpu().numpy(), ref) < 1e-13
+
+
+def test_gather_and_conj(ops):
+    rng = np.random.default_rng(12)
+    src = crand(rng, 2, 11, 301)
+    idx = np.array([[3, -1, 0, 10], [1, 1, -1, 5]], dtype=np.int32)
+    out = ops.gather_rows(dev(src), dev(idx)).cpu().numpy()
+    for z in range(2):
+        for i in range(4):
+            ref = src[z, idx[z, i]] if idx[z, i] >= 0 else np.zeros(301)
+            assert np.array_equal(out[z, i], ref)
+    s = dev(src)
+    d = torch.empty_like(s)
+    ops.conj_copy(s, d)
+    assert np.array_equal(d.cpu().numpy(), src.conj())

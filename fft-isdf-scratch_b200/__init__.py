@@ -4,6 +4,6 @@ Import name: `fft_isdf_scratch_b200` (see the loader shim at the repo root; the 
 name carries a hyphen).  Public surface mirrors /root/reference/fftisdf.py.
 """
 from . import pbc_tools  # noqa: F401
-from .cell import SyntheticCell, random_cubic_cell, diamond_standin, nio_afm_standin  # noqa: F401
+from .cell import SyntheticCell, TableCell, random_cubic_cell, diamond_standin, nio_afm_standin  # noqa: F401
 
-__all__ = ["pbc_tools", "SyntheticCell", "random_cubic_cell", "diamond_standin", "nio_afm_standin"]
+__all__ = ["pbc_tools", "SyntheticCell", "TableCell", "random_cubic_cell", "diamond_standin", "nio_afm_standin"]

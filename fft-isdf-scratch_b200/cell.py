@@ -208,3 +208,44 @@ def nio_afm_standin(mesh=None, ke_cutoff=200.0):
         mesh = pbc_tools.cutoff_to_mesh(a, ke_cutoff)
     cell = SyntheticCell(a, shells, mesh, name="nio-afm-standin")
     return cell
+
+
+class TableCell:
+    """Geometry-only cell whose AO values are supplied as precomputed tables (e.g. dumped from PySCF's
+    `pbc_eval_gto`, or the golden fixtures): use with `ISDF.set_ao_tables(x0=..., f_all=...)`."""
+
+    def __init__(self, a, mesh, nao, name="table-cell"):
+        self.a = np.asarray(a, dtype=np.float64).reshape(3, 3)
+        self.mesh = [int(m) for m in mesh]
+        self._nao = int(nao)
+        self.name = name
+        self.verbose = 0
+        self.max_memory = 160000
+        self.dimension = 3
+        self.low_dim_ft_type = None
+
+    def lattice_vectors(self):
+        return self.a
+
+    @property
+    def vol(self):
+        return float(abs(np.linalg.det(self.a)))
+
+    def nao_nr(self):
+        return self._nao
+
+    def make_kpts(self, kmesh):
+        return pbc_tools.make_kpts(self.a, kmesh)
+
+    get_kpts = make_kpts
+
+    def gen_uniform_grids(self, mesh=None, wrap_around=False):
+        return pbc_tools.gen_uniform_grids(self.a, self.mesh if mesh is None else mesh, wrap_around)
+
+    get_uniform_grids = gen_uniform_grids
+
+    def get_Gv(self, mesh=None):
+        return pbc_tools.get_Gv(self.a, self.mesh if mesh is None else mesh)
+
+    def pbc_eval_gto(self, *args, **kwargs):
+        raise RuntimeError("TableCell has no basis: supply AO tables with ISDF.set_ao_tables()")

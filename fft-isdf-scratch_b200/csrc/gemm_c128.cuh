@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(GemmParams p
         } else if (EPI == EPI_HERK) {
           if (r >= c) {
             const int pr = perm ? perm[r] : r, pc = perm ? perm[c] : c;
-            Cb[(long)pr * p.ldc + pc] = make_double2(alpha * vr, alpha * vi);
+            // the diagonal of B B^H is real: store an exact zero imaginary part
+            Cb[(long)pr * p.ldc + pc] = make_double2(alpha * vr, (r == c) ? 0.0 : alpha * vi);
             if (r > c) Cb[(long)pc * p.ldc + pr] = make_double2(alpha * vr, -alpha * vi);
           }
         } else {  // EPI_SQ_SYM: out = alpha * re^2 (real, stored as complex with zero imaginary part)

@@ -1,0 +1,422 @@
+"""Host-side mirror of /root/reference/fftisdf.py for the B200 ISDF build.
+
+Same call surface as the reference (names, argument meaning, attributes, error behaviour):
+
+    df = ISDF(cell, kpts, m0=None, c0=20.0); df.build()      # fftisdf.py:302-325
+    df._x [nk,nip,nao], df._w0 [nip,nip], df._wq [nk,nip,nip]  (complex128 numpy, fftisdf.py:125-128)
+    df.get_jk(dm, ...)  ->  get_j_kpts / get_k_kpts           # fftisdf.py:133-228,390-408
+
+`cell` is a pyscf.pbc.gto.Cell (when PySCF is importable) or any duck-typed equivalent such as
+`SyntheticCell`.  All O(ng*nip) arithmetic runs in libisdf_b200.so (hand-written sm_100a kernels
+through the C ABI in include/isdf_b200.h); this module only sequences stages, owns device buffers
+(torch tensors) and builds O(ng)/O(nk^2) tables.  There is no CPU fallback: without the library or
+without a B200 the constructor raises.
+
+Deliberate differences from the reference, all documented in DESIGN.md:
+  * `kpts = self.cell.get_kpts(kmesh)` uses self.cell (the reference reads a module global, :322).
+  * W_q is formed in G space, W_q = B B^H with B = FFT[Theta_q e^{-iq.r}] sqrt(v(q+G) vol)/ng, which is
+    algebraically identical to :113-121 (Parseval) and Hermitian by construction.
+  * A_q Theta_q = Y_q^T is solved by a rank-revealing (diagonally pivoted) Cholesky factorisation
+    instead of LAPACK zgelsy; identical to rounding when A_q is numerically full rank.
+  * only one of each time-reversal pair (q, -q) is computed; the partner is the complex conjugate.
+  * additive attributes: `_mask` (interpolation-point indices), `_ranks`, `_theta` (optional).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy
+import torch
+
+from . import pbc_tools
+from .kernels import IsdfOps, TB
+
+try:  # pragma: no cover - PySCF is not in the build image
+    from pyscf.pbc.df.fft import FFTDF as _Base
+    _HAVE_PYSCF = True
+except Exception:  # noqa: BLE001
+    _HAVE_PYSCF = False
+
+    class _Grids:
+        def __init__(self, cell):
+            self.cell = cell
+            self.coords = cell.gen_uniform_grids(cell.mesh)
+            self.non0tab = True
+
+    class _Base:  # the handful of FFTDF members the reference hot path reads
+        def __init__(self, cell, kpts=numpy.zeros((1, 3))):
+            self.cell = cell
+            self.kpts = numpy.asarray(kpts).reshape(-1, 3)
+            self.mesh = list(cell.mesh)
+            self.grids = _Grids(cell)
+            self.verbose = getattr(cell, "verbose", 0)
+            self.max_memory = getattr(cell, "max_memory", 4000)
+
+_OPS = {}
+
+
+def _get_ops(device):
+    if device not in _OPS:
+        _OPS[device] = IsdfOps(device)
+    return _OPS[device]
+
+
+def _log(df_obj, msg, *args):
+    if getattr(df_obj, "verbose", 0) >= 4:
+        print(msg % args, flush=True)
+
+
+def _to_dev(ops, arr, pinned=True):
+    """Host numpy -> device tensor through a pinned staging buffer (counted in df_obj._h2d_bytes)."""
+    t = torch.from_numpy(numpy.ascontiguousarray(arr))
+    if pinned:
+        t = t.pin_memory()
+    return t.to(ops.device, non_blocking=True)
+
+
+def _time_reversal_valid(kmesh, mesh, coulg_all, partner):
+    """W_{-q} = conj(W_q) holds iff the Coulomb weights satisfy v_{q'}(G') = v_q(-G'-G0) on the FFT
+    index grid (q' = -q + G0).  True for odd meshes; even meshes break it at the Nyquist planes
+    (and PySCF's get_coulG wrap-around is asymmetric there), so the pair is then computed twice."""
+    n1, n2, n3 = mesh
+    nk = len(partner)
+    j = pbc_tools.cartesian_prod([numpy.arange(n) for n in kmesh])
+    ok = numpy.zeros(nk, dtype=bool)
+    i1, i2, i3 = numpy.meshgrid(numpy.arange(n1), numpy.arange(n2), numpy.arange(n3), indexing="ij")
+    for q in range(nk):
+        qp = int(partner[q])
+        if qp == q:
+            continue
+        g0 = (j[q] != 0).astype(int)  # q + q' = G0 (in units of b)
+        idx = (((-i1 - g0[0]) % n1) * n2 + ((-i2 - g0[1]) % n2)) * n3 + ((-i3 - g0[2]) % n3)
+        vq, vqp = coulg_all[q], coulg_all[qp]
+        ok[q] = bool(numpy.abs(vqp - vq[idx.ravel()]).max() <= 1e-12 * max(numpy.abs(vq).max(), 1e-300))
+    for q in range(nk):  # a pair is usable only if the check holds both ways
+        ok[q] = ok[q] and ok[int(partner[q])]
+    return ok
+
+
+def build(df_obj):
+    """B200 restatement of `build(df_obj)` at /root/reference/fftisdf.py:22-128."""
+    ops = df_obj._ops
+    dev = ops.device
+    pcell = df_obj.cell
+    kmesh = df_obj.kmesh
+    vk = numpy.asarray(df_obj.kpts)
+    a = numpy.asarray(pcell.lattice_vectors())
+    phase = pbc_tools.get_phase(a, vk, kmesh)                               # :28
+    if not pbc_tools.phase_is_separable(phase, kmesh):
+        raise NotImplementedError("k-points are not the Gamma-centred regular mesh cell.get_kpts(kmesh)")
+    nao = pcell.nao_nr()
+    nkpt = int(numpy.prod(kmesh))
+    stats = df_obj._stats = dict(h2d_bytes=0, d2h_bytes=0)
+    ev = df_obj._events = {}
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        ev[name] = e
+
+    mark("start")
+    # ---- A. interpolation points                                              :33 -> :357-388
+    xip = df_obj.select_interpolation_points(_device_result=True)
+    nip = xip.shape[1]
+    assert xip.shape == (nkpt, nip, nao)
+    _log(df_obj, "Number of interpolation points = %d", nip)
+    mark("select")
+
+    # ---- B1. metric A_q                                                        :38-48
+    uax = ops.pack_uaxes(kmesh)
+    mesh = [int(m) for m in df_obj.mesh]
+    gv = pcell.get_Gv(mesh)                                                   # :91
+    coulg_all = [pbc_tools.get_coulG(a, vq, mesh, Gv=gv) for vq in vk]       # :114 (O(nk*ng) host tables)
+    partner = pbc_tools.time_reversal_partner(kmesh)
+    use_tr = bool(getattr(df_obj, "use_time_reversal", True))
+    tr_ok = _time_reversal_valid(kmesh, mesh, coulg_all, partner) if use_tr else numpy.zeros(nkpt, bool)
+    qind = [q for q in range(nkpt) if not (tr_ok[q] and partner[q] < q)]
+    nq = len(qind)
+    qslot_h = -numpy.ones(nkpt, dtype=numpy.int32)
+    qslot_h[qind] = numpy.arange(nq, dtype=numpy.int32)
+    qslot = torch.from_numpy(qslot_h).to(dev)
+    diag = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    x2_k = ops.gram_conja(xip, xip)                                          # :38
+    a_q = torch.empty((nq, nip, nip), dtype=torch.complex128, device=dev)
+    ops.ktransform_square(x2_k, nip * nip, nip, a_q, nip * nip, nip, 1, 0, nip, nip, kmesh, uax,
+                          conj2=1, out_g_fast=0, qslot=qslot, diag=diag[0:2])  # :41-47
+    del x2_k
+    if getattr(df_obj, "keep_metric", False):
+        df_obj._a_q = a_q.clone()
+
+    # ---- C(a). rank-revealing Cholesky of every A_q (replaces the QRCP inside zgelsy, :108)
+    rcond = getattr(df_obj, "rcond", -1.0)
+    u_q, piv_q, rank_q, _ = ops.pchol(a_q, max_steps=nip, tol=rcond, nb=df_obj.chol_nb)
+    del a_q
+    nipP = -(-nip // TB) * TB
+    lfwd, ubwd = ops.trsm_prepare(u_q, piv_q, rank_q, nipP)
+    del u_q
+    piv_h = piv_q.cpu().numpy()
+    rank_h = rank_q.cpu().numpy()
+    stats["d2h_bytes"] += piv_h.nbytes + rank_h.nbytes
+    rowmap_h = -numpy.ones((nq, nip), dtype=numpy.int32)
+    for s in range(nq):
+        r = int(rank_h[s])
+        rowmap_h[s, piv_h[s, :r]] = numpy.arange(r, dtype=numpy.int32)
+    rowmap = torch.from_numpy(rowmap_h).to(dev)
+    mark("metric")
+
+    # ---- B2. right-hand side Y_q^T, written straight into pivot order           :72-87
+    grids = df_obj.grids
+    coord = numpy.asarray(grids.coords)
+    ngrid = coord.shape[0]
+    _log(df_obj, "nkpt = %d, ngrid = %d, nip = %d", nkpt, ngrid, nip)
+    theta = torch.zeros((nq, nipP, ngrid), dtype=torch.complex128, device=dev)  # Y^T, then Theta, then B
+    blksize = int(df_obj.blksize)
+    fx_k = None
+    for ao_k_etc, g0, g1 in df_obj.aoR_loop(grids, vk, 0, blksize=blksize):   # :72
+        f_k = ao_k_etc[0]
+        if not torch.is_tensor(f_k):
+            f_k = numpy.asarray(f_k)                                          # :73
+            assert f_k.shape == (nkpt, g1 - g0, nao)
+            stats["h2d_bytes"] += f_k.nbytes
+            f_k = _to_dev(ops, f_k)
+        blk = g1 - g0
+        if fx_k is None or fx_k.shape[1] != blk:
+            fx_k = torch.empty((nkpt, blk, nip), dtype=torch.complex128, device=dev)
+        ops.gram_conja(f_k, xip, out=fx_k)                                    # :76
+        ops.ktransform_square(fx_k, blk * nip, nip, theta, nipP * ngrid, 1, ngrid, g0, blk, nip, kmesh, uax,
+                              conj2=0, out_g_fast=1, qslot=qslot, rowmap=rowmap, rowmap_sq=nip,
+                              diag=diag[2:4])                                 # :79-85
+        _log(df_obj, "finished aoR_loop[%8d:%8d]", g0, g1)
+    del fx_k
+    mark("rhs")
+
+    # ---- C(b). Theta_q = A_q^+ Y_q^T by two blocked triangular sweeps, all q at once  :108
+    ops.trsm_sweeps(lfwd, ubwd, theta)
+    del lfwd, ubwd
+    mark("fit")
+    if getattr(df_obj, "keep_theta", False):
+        df_obj._theta_dev = ops.gather_rows(theta[:, :nip, :].contiguous() if nipP != nip else theta, rowmap)
+
+    # ---- D. Coulomb kernel                                                       :96-122
+    vol = float(pcell.vol)
+    wq = torch.empty((nkpt, nip, nip), dtype=torch.complex128, device=dev)
+    wslot = torch.empty((nq, nip, nip), dtype=torch.complex128, device=dev)
+    for s, q in enumerate(qind):                                              # :97
+        vq = vk[q]
+        fq = numpy.exp(-1j * numpy.dot(coord, vq))                            # :99
+        coulg = coulg_all[q]                                                  # :114
+        wgt = numpy.sqrt(coulg * vol) / ngrid                                 # :115 folded with Parseval's 1/ng
+        ops.fft3d(theta[s], mesh, pre=torch.from_numpy(fq).to(dev), post=torch.from_numpy(wgt).to(dev))  # :113-115
+    mark("fft")
+    ops.herk_strided(theta, ngrid, nipP * ngrid, nip, ngrid, 1.0, piv_q, nip, wslot, nq)  # :121
+    for s, q in enumerate(qind):
+        wq[q].copy_(wslot[s])
+        if partner[q] != q and tr_ok[q]:
+            ops.conj_copy(wslot[s], wq[partner[q]])
+    mark("kernel")
+    del theta, wslot
+
+    d = diag.cpu().numpy()
+    assert d[0] < 1e-10 * max(1.0, d[1]) or d[0] < 1e-10, "abs(x2_s.imag).max() = %g" % d[0]   # :43
+    assert d[2] < 1e-10 * max(1.0, d[3]) or d[2] < 1e-10, "abs(fx_s.imag).max() = %g" % d[2]   # :81
+
+    df_obj._x_dev = xip
+    df_obj._wq_dev = wq
+    df_obj._ranks = rank_h.copy()
+    df_obj._qind = list(qind)
+    x_h = xip.cpu().numpy()
+    wq_h = wq.cpu().numpy()
+    stats["d2h_bytes"] += x_h.nbytes + wq_h.nbytes
+    mark("end")
+    torch.cuda.synchronize(dev)
+    names = ["start", "select", "metric", "rhs", "fit", "fft", "kernel", "end"]
+    df_obj._stage_ms = {names[i + 1]: ev[names[i]].elapsed_time(ev[names[i + 1]]) for i in range(len(names) - 1)}
+    for s, q in enumerate(qind):
+        _log(df_obj, "w[%3d], rank = %4d / %4d", q, int(rank_h[s]), nip)       # :122
+    df_obj._x = x_h                                                            # :125
+    df_obj._w0 = wq_h[0]                                                       # :127
+    df_obj._wq = wq_h                                                          # :128
+
+
+def get_j_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=None, exxdiv=None):
+    """fftisdf.py:133-171 (host numpy on the small [nk,nip,nao] / [nip,nip] outputs of the build)."""
+    assert exxdiv is None
+    kpts = numpy.asarray(kpts)
+    dm_kpts = numpy.asarray(dm_kpts, order="C")
+    nkpt = len(kpts)
+    nao = dm_kpts.shape[-1]
+    dms = dm_kpts.reshape(-1, nkpt, nao, nao)
+    nset = dms.shape[0]
+    assert df_obj._x is not None and df_obj._w0 is not None
+    nip = df_obj._x.shape[1]
+    assert df_obj._x.shape == (nkpt, nip, nao)
+    assert df_obj._w0.shape == (nip, nip)
+    assert kpts_band is None, "kpts_band is not supported (fftisdf.py:164)"
+    rho = numpy.einsum("kIm,kIn,xkmn->xI", df_obj._x, df_obj._x.conj(), dms, optimize=True)
+    rho *= 1.0 / nkpt
+    v = numpy.einsum("IJ,xJ->xI", df_obj._w0, rho, optimize=True)
+    vj_kpts = numpy.einsum("kIm,kIn,xI->xkmn", df_obj._x.conj(), df_obj._x, v, optimize=True)
+    assert vj_kpts.shape == (nset, nkpt, nao, nao)
+    if abs(kpts).max() < 1e-9:
+        vj_kpts = vj_kpts.real
+    return vj_kpts.reshape(dm_kpts.shape)
+
+
+def get_k_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=None, exxdiv=None):
+    """fftisdf.py:173-228."""
+    assert exxdiv is None
+    assert kpts_band is None, "kpts_band is not supported (fftisdf.py:194)"
+    pcell = df_obj.cell
+    kmesh = df_obj.kmesh
+    phase = pbc_tools.get_phase(numpy.asarray(pcell.lattice_vectors()), df_obj.kpts, kmesh)
+    dm_kpts = numpy.asarray(dm_kpts, order="C")
+    nkpt = len(numpy.asarray(kpts))
+    nao = dm_kpts.shape[-1]
+    dms = dm_kpts.reshape(-1, nkpt, nao, nao)
+    nset = dms.shape[0]
+    nip = df_obj._x.shape[1]
+    assert df_obj._x.shape == (nkpt, nip, nao)
+    assert df_obj._wq.shape == (nkpt, nip, nip)
+    ws = phase @ df_obj._wq.reshape(nkpt, -1)
+    ws = ws.reshape(nkpt, nip, nip)
+    ws = ws.real * numpy.sqrt(nkpt)
+    vk_kpts = []
+    for dm in dms:
+        rhok = numpy.asarray([x @ d @ x.conj().T for x, d in zip(df_obj._x, dm)]) / nkpt
+        rhos = phase @ rhok.reshape(nkpt, -1)
+        assert abs(rhos.imag).max() < 1e-10
+        rhos = rhos.real.reshape(nkpt, nip, nip)
+        vs = ws * rhos.transpose(0, 2, 1)
+        vk = (phase.T @ vs.reshape(nkpt, -1)).reshape(nkpt, nip, nip)
+        vk_kpts.append([x.conj().T @ v @ x for x, v in zip(df_obj._x, vk)])
+    vk_kpts = numpy.asarray(vk_kpts).reshape(nset, nkpt, nao, nao)
+    return vk_kpts.reshape(dm_kpts.shape)
+
+
+class InterpolativeSeparableDensityFitting(_Base):
+    _x = None
+    _w0 = None
+    _wq = None
+    blksize = 8000   # block size for the aoR_loop            (fftisdf.py:300)
+    chol_nb = 32     # panel width of the pivoted Cholesky kernels
+
+    def __init__(self, cell, kpts, m0=None, c0=20.0, device=0):
+        super().__init__(cell, kpts)
+        self.m0 = m0 if m0 is not None else [15, 15, 15]       # :305
+        self.c0 = c0                                            # :306
+        self._ops = _get_ops(device)                            # raises without libisdf_b200.so / B200
+        self._ao_cache = None
+
+    def build(self):
+        a = numpy.asarray(self.cell.lattice_vectors())
+        kmesh = pbc_tools.kpts_to_kmesh(a, self.kpts)           # :317-318
+        self.kmesh = kmesh                                      # :319
+        self.kpts = self.cell.get_kpts(kmesh)                   # :322 (self.cell, not the module global)
+        _log(self, "transformed kmesh = %s", kmesh)
+        return build(self)
+
+    def aoR_loop(self, grids=None, kpts=None, deriv=0, blksize=None):
+        """fftisdf.py:327-355: yields (ao_k_etc, p0, p1); ao_k_etc[0] = per-k [blk, nao] AO values,
+        ao_k_etc[4] = coords.  PySCF's NumInt.block_loop when available, else cell.pbc_eval_gto."""
+        if grids is None:
+            grids = self.grids
+        cell = self.cell
+        if blksize is None:
+            blksize = self.blksize
+        if kpts is None:
+            kpts = self.kpts
+        kpts = numpy.asarray(kpts)
+        assert getattr(cell, "dimension", 3) == 3
+        if _HAVE_PYSCF and hasattr(self, "_numint") and not hasattr(cell, "_images"):
+            if grids.non0tab is None:
+                grids.build(with_non0tab=True)
+            p1 = 0
+            for ao_k1_etc in self._numint.block_loop(cell, grids, cell.nao_nr(), deriv, kpts,
+                                                     max_memory=max(2000, self.max_memory), blksize=blksize):
+                coords = ao_k1_etc[4]
+                p0, p1 = p1, p1 + coords.shape[0]
+                yield ao_k1_etc, p0, p1
+            return
+        coords_all = numpy.asarray(grids.coords)
+        ao_all = getattr(self, "_ao_tables", None)
+        for p0 in range(0, len(coords_all), blksize):
+            p1 = min(len(coords_all), p0 + blksize)
+            c = coords_all[p0:p1]
+            if ao_all is not None:
+                ao = ao_all[:, p0:p1, :]
+            else:
+                ao = numpy.asarray(cell.pbc_eval_gto("GTOval", c, kpts=kpts))
+            yield (ao, ao, None, None, c), p0, p1
+
+    def set_ao_tables(self, x0=None, f_all=None):
+        """Optional: hand the build precomputed AO tables (x0 [nk,n0,nao] on the parent grid m0,
+        f_all [nk,ng,nao] on the dense grid; numpy host arrays or CUDA tensors)."""
+        self._x0_table = x0
+        self._ao_tables = f_all
+
+    def select_interpolation_points(self, x0=None, phase=None, _device_result=False):
+        """fftisdf.py:357-388.  Returns x0[:, mask, :]; also sets self._mask, self._chol_rank,
+        self._chol_next (the reference logs chol[nip, nip])."""
+        ops = self._ops
+        c0 = self.c0
+        m0 = self.m0
+        pcell = self.cell
+        nao = pcell.nao_nr()
+        if x0 is None:
+            x0 = getattr(self, "_x0_table", None)
+        if x0 is None:
+            x0 = pcell.pbc_eval_gto("GTOval", pcell.gen_uniform_grids(m0), kpts=self.kpts)   # :367-370
+            x0 = numpy.asarray(x0)                                                         # :371
+        if not torch.is_tensor(x0):
+            if hasattr(self, "_stats"):
+                self._stats["h2d_bytes"] += x0.nbytes
+            x0 = _to_dev(ops, x0)
+        nkpt, ng = x0.shape[:2]                                                            # :373
+        assert x0.shape == (nkpt, ng, nao)                                                 # :374
+        x4 = ops.select_gram(x0)                                                           # :376-379
+        nmax = min(int(nao * c0), ng)
+        u, piv, rank, nxt = ops.pchol(x4.reshape(1, ng, ng), max_steps=nmax, tol=-1.0, nb=self.chol_nb)  # :381-382
+        del u, x4
+        nip = int(rank.cpu()[0])                                                           # :383  min(int(nao*c0), rank)
+        mask = piv[0, :nip].contiguous()                                                   # :384
+        self._mask = mask.cpu().numpy().astype(numpy.int64)
+        self._chol_rank = nip
+        self._chol_next = float(nxt.cpu()[0])
+        _log(self, "Pivoted Cholesky rank >= %d, nip = %d, estimated error = %6.2e", nip, nip,
+             numpy.sqrt(max(self._chol_next, 0.0)))                                         # :387
+        xip = ops.gather_rows(x0, mask.reshape(1, nip).expand(nkpt, nip).contiguous())      # :388
+        if _device_result:
+            return xip
+        return xip.cpu().numpy()
+
+    def get_jk(self, dm, hermi=1, kpts=None, kpts_band=None, with_j=True, with_k=True, omega=None, exxdiv=None):
+        """fftisdf.py:390-408."""
+        if omega is not None:
+            raise NotImplementedError
+        if exxdiv is not None:
+            raise NotImplementedError
+        kpts = self.kpts if kpts is None else numpy.asarray(kpts).reshape(-1, 3)
+        if len(kpts) == 1 and numpy.asarray(dm).ndim == 2:
+            raise NotImplementedError  # single k-point call (fftisdf.py:400-401)
+        vj = vk = None
+        if with_k:
+            vk = get_k_kpts(self, dm, hermi, kpts, kpts_band, exxdiv)
+        if with_j:
+            vj = get_j_kpts(self, dm, hermi, kpts, kpts_band)
+        return vj, vk
+
+
+ISDF = InterpolativeSeparableDensityFitting
+
+
+def get_coul(df_obj, kmesh=None, c0=20.0, m0=None, blksize=8000, device=0):
+    """Function-form twin of /root/reference/fftdf-with-k-lstsq.py:20-189:
+    returns (coul_q [nk,nip,nip], x_k [nk,nip,nao])."""
+    if kmesh is None:
+        kmesh = [1, 1, 1]
+    cell = df_obj.cell
+    isdf = ISDF(cell, cell.get_kpts(kmesh), m0=m0, c0=c0, device=device)
+    isdf.blksize = blksize
+    isdf.build()
+    return isdf._wq, isdf._x

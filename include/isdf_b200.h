@@ -1,0 +1,100 @@
+/* libisdf_b200 -- C ABI of the B200-native FFT-ISDF build (sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of yangjunjie0320/fft-isdf-scratch:
+ * `build(df_obj)` (fftisdf.py:22-128) and `select_interpolation_points` (fftisdf.py:357-388).
+ * The reference is pure Python; the native kernels it reaches through numpy/scipy/PySCF
+ * (ZGEMM, dpstrf, zgelsy, FFT) are what the entry points below replace, one per call site.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, < 0 = argument error, > 0 = cudaError_t;
+ *     isdf_last_error(handle) gives the message.  Nothing throws across the ABI.
+ *   - all pointers are DEVICE pointers owned by the caller unless stated otherwise; complex128 is
+ *     interleaved (re, im) doubles exactly as numpy / torch store it; matrices are row-major.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *   - one handle per (process, device); a handle is not thread-safe.  The handle owns only small
+ *     plans (FFT twiddle tables).
+ *   - there is no CPU path: isdf_create fails on anything that is not compute capability 10.x.
+ */
+#ifndef ISDF_B200_H
+#define ISDF_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int isdf_abi_version(void);
+int isdf_create(int device, void** handle_out);
+int isdf_destroy(void* handle);
+const char* isdf_last_error(void* handle);
+
+/* fftisdf.py:376-379   x2 = sum_q Re(x0[q]^* x0[q]^T);  x4 = x2*x2/nkpt
+ * x0 [nk][n0][nao] c128  ->  x4c [n0][n0] c128 with zero imaginary parts (exactly symmetric). */
+int isdf_select_gram(void* handle, const void* x0, int nk, int n0, int nao, void* x4c, void* stream);
+
+/* fftisdf.py:381-382  pyscf.lib.scipy_helper.pivoted_cholesky -> LAPACK dpstrf (upper), and the
+ * rank-revealing factorisation used in place of the QRCP inside scipy lstsq(..., "gelsy") at :108.
+ * a [batch][n][n] Hermitian PSD (destroyed).  Runs at most max_steps pivots, stops earlier when the
+ * pivot <= tol (tol < 0: n*eps*max diag, LAPACK's default).  nb = panel width (<= 64, 0 -> 32).
+ * u [batch][ldu_rows][n]: row j = row j of U (A = U^H U) in ORIGINAL column order.
+ * piv [batch][n] (0-based, position -> original index), rank [batch], next_pivot [batch] (value of the
+ * pivot that would come next; sqrt of it is the reference's chol[nip,nip] at :387), may be NULL.
+ * workspace: isdf_pchol_workspace_bytes(n, batch) bytes. */
+int isdf_pchol_workspace_bytes(int n, int batch, size_t* bytes);
+int isdf_pchol(void* handle, void* a, int n, int batch, int max_steps, double tol, int nb, void* u, int ldu_rows,
+               int* piv, int* rank, double* next_pivot, void* workspace, void* stream);
+
+/* fftisdf.py:38 (x2_k) and :76 (fx_k):  c[z][i][j] = sum_l conj(a[z][i][l]) * b[z][j][l]
+ * a [m][k] (ld lda), b [n][k] (ld ldb), c [m][n] (ld ldc); batch strides in elements. */
+int isdf_gram_conja(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                    void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream);
+
+/* plain batched complex GEMM c[z] = a[z] b[z], a [m][k], b [k][n] (the kernel behind the sweeps). */
+int isdf_gemm_nn(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                 void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream);
+
+/* fftisdf.py:41-47 (metric, conj2=1) and :79-85 (right-hand side, conj2=0):
+ *   s = phase @ v;  assert |Im s| small;  y = s*s;  out = phase^H @ y  or  phase^T @ y
+ * in[k*in_sk + g*in_sg + i], g < ng, i < ni;  kmesh[3] (host) with every axis <= 8;
+ * uaxes: device, 3 matrices [8][8] c128, U_a[m][j] = exp(2 pi i m j/N_a)/sqrt(N_a) (phase = U1 x U2 x U3);
+ * out[slot*out_sq + (out_g0+g)*out_sg + row*out_si], slot = qslot[q] (NULL: q; <0: skip),
+ * row = rowmap[slot*rowmap_sq + i] (NULL: i; <0: drop);  out_g_fast = 1 when out_sg == 1.
+ * diag (device, 2 doubles, may be NULL): running max of |Im s| and |Re s| (atomic max). */
+int isdf_ktransform_square(void* handle, const void* in, long in_sk, long in_sg, void* out, long out_sq, long out_sg,
+                           long out_si, long out_g0, int ng, int ni, const int* kmesh, const void* uaxes, int conj2,
+                           int out_g_fast, const int* qslot, const int* rowmap, long rowmap_sq, double* diag,
+                           void* stream);
+
+/* fftisdf.py:108  scipy.linalg.lstsq(A_q, Y_q^T): block operators of the two triangular sweeps from the
+ * pivoted factor (block size 64).  n = nip, nP = n rounded up to 64.  lfwd, ubwd [batch][nP][nP];
+ * work 2*batch*nP*nP c128.  Rows/columns at positions >= rank are replaced by the identity. */
+int isdf_trsm_prepare(void* handle, const void* u, int ldu_rows, const int* piv, const int* rank, int n, int nP,
+                      int batch, void* lfwd, void* ubwd, void* work, void* stream);
+/* In place T <- U^{-1} U^{-H} T on t [batch][nP][ldt] (ng columns used): Theta in pivot order. */
+int isdf_trsm_sweeps(void* handle, const void* lfwd, const void* ubwd, void* t, int nP, long ng, long ldt, int batch,
+                     void* stream);
+
+/* fftisdf.py:113-115  pbctools.fft(z_q * fq, mesh) * coulG * vol/ngrid  (the ifft at :118 is removed by
+ * Parseval):  data [nvec][ng] in place, out[v][G] = post[G] * sum_r data[v][r] pre[r] e^{-iG.r}.
+ * mesh[3] host; pre [ng] c128 or NULL; post [ng] f64 or NULL; group_vecs <= 0 picks an L2-sized group. */
+int isdf_fft3d_batched(void* handle, void* data, long nvec, const int* mesh, const void* pre, const double* post,
+                       long group_vecs, void* stream);
+int isdf_fft_release_plans(void* handle);
+
+/* fftisdf.py:121  W_q = zeta_q @ z_q^H  in Parseval form:
+ * w[z][perm[i]][perm[j]] = alpha * sum_g b[z][i][g] conj(b[z][j][g]);  exactly Hermitian output.
+ * perm [batch][stridePerm...] position -> original index, or NULL. */
+int isdf_herk_scatter(void* handle, const void* b, long ldb, long strideB, int n, int k, double alpha,
+                      const int* perm, long stridePerm, void* w, long ldw, long strideW, int batch, void* stream);
+
+/* data movement: dst = conj(src) (time-reversal partner W_{-q} = W_q^*), and row gather
+ * dst[z][i][:] = src[z][idx[z][i]][:] (zeros where idx < 0)  (fftisdf.py:388 x0[:, mask, :]). */
+int isdf_conj_copy(void* handle, const void* src, void* dst, long n, void* stream);
+int isdf_gather_rows(void* handle, const void* src, long lds, long strideS, const int* idx, long strideI, int nrows,
+                     long ncols, void* dst, long ldd, long strideD, int batch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISDF_B200_H */

@@ -156,6 +156,10 @@ CASES = {
     "k222_sp": dict(mesh=[9, 9, 9], nao=6, seed=12, kmesh=[2, 2, 2], m0=[6, 6, 6], c0=5.0, ltypes="sp", blksize=250),
     "k321_spd": dict(mesh=[8, 9, 10], nao=8, seed=13, kmesh=[3, 2, 1], m0=[5, 6, 7], c0=4.0, ltypes="spd", blksize=8000,
                      skew=True),
+    # odd mesh (what PySCF's cutoff_to_mesh produces), skewed lattice, nip below the local pair rank:
+    # numerically full-rank A_q and exact time-reversal symmetry W_{-q} = W_q^*
+    "k231_odd": dict(mesh=[9, 11, 7], nao=8, seed=14, kmesh=[2, 3, 1], m0=[6, 7, 5], c0=3.0, ltypes="spd", blksize=500,
+                     skew=True),
 }
 
 

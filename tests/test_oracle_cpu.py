@@ -1,0 +1,135 @@
+"""CPU suite: the oracle against the reference-generated golden vectors, host helpers, and the
+C-ABI library's exported symbols (no compute calls -- there is no GPU here)."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import isdf_oracle as O
+from oracle import pbc_helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ref_*.npz")))
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 3
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_matches_reference_golden(path):
+    """oracle.build == the reference's own build() (fftisdf.py:22-128) on the stored inputs.
+    Both issue the same LAPACK/FFT calls, so agreement is to rounding (1e-12 relative)."""
+    g = np.load(path)
+    out = O.build(g["a"], g["kpts"], g["kmesh"].tolist(), g["mesh"].tolist(), g["x0"], g["f_all"], g["coord"],
+                  float(g["c0"]), blksize=int(g["blksize"]))
+    assert np.array_equal(out["mask"], g["mask"])
+    assert np.abs(out["x"] - g["x"]).max() == 0.0
+    assert np.abs(out["wq"] - g["wq"]).max() <= 1e-12 * np.abs(g["wq"]).max()
+    ph = H.get_phase(g["a"], g["kpts"], g["kmesh"].tolist())
+    dms = g["dm"][None]
+    vj = O.get_j_kpts(out["x"], out["wq"][0], dms)[0]
+    vk = O.get_k_kpts(out["x"], out["wq"], dms, ph)[0]
+    assert np.abs(vj - g["vj"]).max() <= 1e-12 * np.abs(g["vj"]).max()
+    assert np.abs(vk - g["vk"]).max() <= 1e-12 * np.abs(g["vk"]).max()
+
+
+def test_phase_is_unitary_dft():
+    """P @ . is the unitary inverse DFT over the k-mesh axes; P is symmetric."""
+    a = np.eye(3) * 5.0 + 0.2
+    kmesh = [3, 2, 4]
+    ph = H.get_phase(a, H.get_kpts(a, kmesh), kmesh)
+    x = np.random.default_rng(0).standard_normal((24, 7)) + 0j
+    ref = np.fft.ifftn(x.reshape(3, 2, 4, 7), axes=(0, 1, 2), norm="ortho").reshape(24, 7)
+    assert np.abs(ph @ x - ref).max() < 1e-13
+    assert np.abs(ph - ph.T).max() < 1e-13
+
+
+def test_parseval_form_of_w():
+    """zeta @ Theta^H == B B^H with B = FFT[Theta fq] sqrt(v vol)/ng."""
+    g = np.load(GOLDEN[1])
+    a, kpts, mesh = g["a"], g["kpts"], g["mesh"].tolist()
+    rng = np.random.default_rng(1)
+    ng = len(g["coord"])
+    th = rng.standard_normal((7, ng)) + 1j * rng.standard_normal((7, ng))
+    q = 3
+    fq = np.exp(-1j * g["coord"] @ kpts[q])
+    cg = H.get_coulG(a, kpts[q], mesh)
+    vol = abs(np.linalg.det(a))
+    zeta = H.ifft(H.fft(th * fq, mesh) * cg * vol / ng, mesh) * fq.conj()
+    w_ref = zeta @ th.conj().T
+    b = H.fft(th * fq, mesh) * np.sqrt(cg * vol) / ng
+    assert np.abs(b @ b.conj().T - w_ref).max() < 1e-13 * np.abs(w_ref).max()
+
+
+def test_time_reversal_symmetry_of_w():
+    """W_{-q} = conj(W_q) in the reference's own output -- for odd FFT meshes with
+    numerically full-rank A_q; the host check that gates the shortcut must agree."""
+    import fft_isdf_scratch_b200 as pk
+    from fft_isdf_scratch_b200.fftisdf import _time_reversal_valid
+    T = pk.pbc_tools
+    for name, expect in [("k231_odd", True), ("k321_spd", False)]:
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz"))
+        kmesh, mesh = g["kmesh"].tolist(), g["mesh"].tolist()
+        part = T.time_reversal_partner(kmesh)
+        coulg = [T.get_coulG(g["a"], k, mesh) for k in g["kpts"]]
+        ok = _time_reversal_valid(kmesh, mesh, coulg, part)
+        wq = g["wq"]
+        for q in range(len(part)):
+            if part[q] == q:
+                continue
+            assert bool(ok[q]) == expect
+            if ok[q]:
+                assert np.abs(wq[part[q]] - wq[q].conj()).max() < 1e-11 * np.abs(wq[q]).max()
+
+
+def test_pivot_rule_restatement_matches_dpstrf():
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((150, 30))
+    x4 = (x @ x.T) ** 2
+    _, piv, rank = H.pivoted_cholesky(x4.copy())
+    p2, steps, _ = H.pivoted_cholesky_steps(x4, 100)
+    assert steps == 100 and np.array_equal(p2, piv[:100])
+
+
+def test_product_helpers_match_oracle_helpers():
+    import fft_isdf_scratch_b200 as pk
+    T = pk.pbc_tools
+    a = np.array([[6.0, 0.4, 0.0], [0.1, 5.0, 0.3], [0.0, -0.2, 7.0]])
+    kmesh, mesh = [2, 3, 2], [7, 8, 9]
+    kp = T.make_kpts(a, kmesh)
+    assert np.abs(kp - H.get_kpts(a, kmesh)).max() < 1e-14
+    assert np.abs(T.get_phase(a, kp, kmesh) - H.get_phase(a, kp, kmesh)).max() < 1e-14
+    assert T.phase_is_separable(T.get_phase(a, kp, kmesh), kmesh)
+    assert np.abs(T.get_Gv(a, mesh) - H.get_Gv(a, mesh)).max() < 1e-13
+    assert np.abs(T.gen_uniform_grids(a, mesh) - H.gen_uniform_grids(a, mesh)).max() < 1e-13
+    for k in kp:
+        assert np.abs(T.get_coulG(a, k, mesh) - H.get_coulG(a, k, mesh)).max() < 1e-12
+    assert T.kpts_to_kmesh(a, kp) == kmesh
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import fft_isdf_scratch_b200._cabi as cabi
+    hdr = open(os.path.join(ROOT, "include", "isdf_b200.h")).read()
+    declared = set(re.findall(r"\b(isdf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert os.path.exists(cabi.lib_path()), "libisdf_b200.so not built: run __graft_entry__.build()"
+    lib = ctypes.CDLL(cabi.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/isdf_b200.h but not exported"
+    assert declared == set(cabi.SIGNATURES), (declared ^ set(cabi.SIGNATURES))
+    assert lib.isdf_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import fft_isdf_scratch_b200 as pk
+    from fft_isdf_scratch_b200 import fftisdf
+    cell = pk.random_cubic_cell(8, 3, seed=0, L=6.0)
+    with pytest.raises(Exception):
+        fftisdf.ISDF(cell, cell.get_kpts([1, 1, 1]))

@@ -139,7 +139,7 @@ def test_trsm_solve(ops, n, ng):
         got = np.zeros_like(ref)
         got[pivh[z]] = sol[z, :n]
         assert relerr(got, ref) < 1e-10
-        assert np.abs(sol[z, n:]).max() == 0.0
+        assert nP == n or np.abs(sol[z, n:]).max() == 0.0
 
 
 @pytest.mark.parametrize("kmesh", [[1, 1, 1], [2, 2, 2], [3, 2, 1], [4, 4, 4], [1, 5, 3]])

@@ -194,14 +194,14 @@ static int get_plan(Handle* h, int n, FftPlan** plan) {
   return ISDF_OK;
 }
 
-static int launch_pass(Handle* h, cplx* data, long nvec, long ng, int n, long stride, long line_step,
+static int launch_pass(Handle* h, cplx* data, long nvec, long ldv, int n, long stride, long line_step,
                        int lines_per_run, long run_stride, int nruns, int contig, const cplx* pre, const double* post,
                        cudaStream_t st) {
   FftPlan* pl;
   int rc = get_plan(h, n, &pl);
   if (rc != ISDF_OK) { snprintf(h->err, sizeof(h->err), "fft plan for n=%d failed (%d)", n, rc); return rc; }
   FftParams p;
-  p.data = data; p.vec_stride = ng; p.n = n; p.stride = stride; p.line_step = line_step;
+  p.data = data; p.vec_stride = ldv; p.n = n; p.stride = stride; p.line_step = line_step;
   p.lines_per_run = lines_per_run; p.run_stride = run_stride; p.nruns = nruns; p.contig = contig;
   p.nstages = pl->nstages;
   for (int i = 0; i < FFT_MAXSTAGES; ++i) p.radix[i] = (i < pl->nstages) ? pl->radix[i] : 1;
@@ -231,9 +231,9 @@ static int launch_pass(Handle* h, cplx* data, long nvec, long ng, int n, long st
 
 using namespace isdf;
 
-// data: [nvec][ng] c128 in place; forward (e^{-i}) unnormalised transform over mesh (C order, z fastest);
+// data: [nvec][ldv >= ng] c128 in place; forward (e^{-i}) unnormalised transform over mesh (C order, z fastest);
 // out[v][G] = post[G] * sum_r data[v][r] * pre[r] * e^{-i G.r}.   group_vecs: vectors per L2-resident group.
-extern "C" int isdf_fft3d_batched(void* hv, void* data, long nvec, const int* mesh, const void* pre_dev,
+extern "C" int isdf_fft3d_batched(void* hv, void* data, long nvec, long ldv, const int* mesh, const void* pre_dev,
                                   const double* post_dev, long group_vecs, void* stream) {
   Handle* h = (Handle*)hv;
   cudaStream_t st = (cudaStream_t)stream;
@@ -241,6 +241,7 @@ extern "C" int isdf_fft3d_batched(void* hv, void* data, long nvec, const int* me
   const int n1 = mesh[0], n2 = mesh[1], n3 = mesh[2];
   ISDF_CHECK_ARG(h, n1 >= 1 && n2 >= 1 && n3 >= 1, "mesh");
   const long ng = (long)n1 * n2 * n3;
+  ISDF_CHECK_ARG(h, ldv >= ng, "ldv < prod(mesh)");
   if (nvec <= 0) return ISDF_OK;
   if (group_vecs <= 0) {
     group_vecs = (long)(48.0 * 1024 * 1024 / ((double)ng * sizeof(cplx)));
@@ -248,21 +249,21 @@ extern "C" int isdf_fft3d_batched(void* hv, void* data, long nvec, const int* me
   }
   for (long v0 = 0; v0 < nvec; v0 += group_vecs) {
     const long nv = (nvec - v0 < group_vecs) ? (nvec - v0) : group_vecs;
-    cplx* d = (cplx*)data + v0 * ng;
+    cplx* d = (cplx*)data + v0 * ldv;
     int rc;
     // z: contiguous lines, n1*n2 of them per vector
     if (n3 > 1 || pre_dev) {
-      rc = launch_pass(h, d, nv, ng, n3, 1, n3, n1 * n2, 0, 1, 1, (const cplx*)pre_dev, (n1 == 1 && n2 == 1) ? post_dev : nullptr, st);
+      rc = launch_pass(h, d, nv, ldv, n3, 1, n3, n1 * n2, 0, 1, 1, (const cplx*)pre_dev, (n1 == 1 && n2 == 1) ? post_dev : nullptr, st);
       if (rc) return rc;
     }
     // y: stride n3, runs over x
     if (n2 > 1) {
-      rc = launch_pass(h, d, nv, ng, n2, n3, 1, n3, (long)n2 * n3, n1, 0, nullptr, (n1 == 1) ? post_dev : nullptr, st);
+      rc = launch_pass(h, d, nv, ldv, n2, n3, 1, n3, (long)n2 * n3, n1, 0, nullptr, (n1 == 1) ? post_dev : nullptr, st);
       if (rc) return rc;
     }
     // x: stride n2*n3, one run of n2*n3 lines
     if (n1 > 1) {
-      rc = launch_pass(h, d, nv, ng, n1, (long)n2 * n3, 1, n2 * n3, 0, 1, 0, nullptr, post_dev, st);
+      rc = launch_pass(h, d, nv, ldv, n1, (long)n2 * n3, 1, n2 * n3, 0, 1, 0, nullptr, post_dev, st);
       if (rc) return rc;
     }
   }

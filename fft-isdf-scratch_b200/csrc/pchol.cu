@@ -379,7 +379,8 @@ extern "C" int isdf_trsm_prepare(void* hv, const void* u, int ldu_rows, const in
   Handle* h = (Handle*)hv;
   cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, u && piv && rank && lfwd && ubwd && work, "null pointer");
-  ISDF_CHECK_ARG(h, nP % TB == 0 && nP >= n && n >= 1, "nP must be a multiple of 64 and >= n");
+  // nP may be smaller than n when every rank[b] <= nP (rows beyond the largest rank are never used)
+  ISDF_CHECK_ARG(h, nP % TB == 0 && nP >= TB && n >= 1, "nP must be a positive multiple of 64");
   ISDF_CHECK_ARG(h, batch >= 1 && batch <= 65535, "batch");
   cplx* Up = (cplx*)work;
   cplx* Lp = Up + (long)batch * nP * nP;

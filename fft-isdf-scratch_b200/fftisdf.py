@@ -28,7 +28,7 @@ import time
 import numpy
 import torch
 
-from . import pbc_tools
+from . import pbc_tools, sharding
 from .kernels import IsdfOps, TB
 
 try:  # pragma: no cover - PySCF is not in the build image
@@ -97,9 +97,17 @@ def _time_reversal_valid(kmesh, mesh, coulg_all, partner):
 
 
 def build(df_obj):
-    """B200 restatement of `build(df_obj)` at /root/reference/fftisdf.py:22-128."""
+    """B200 restatement of `build(df_obj)` at /root/reference/fftisdf.py:22-128.
+
+    Multi-GPU (df_obj.comm = a torch.distributed group, one process per GPU): the dense grid is
+    sharded by contiguous column ranges for the right-hand side and the triangular sweeps, the
+    interpolation vectors for the FFT, with one all-to-all each way and one all-reduce of W_q
+    (sharding.py).  The small per-q factorisations are distributed round-robin and all-gathered.
+    """
     ops = df_obj._ops
     dev = ops.device
+    comm = getattr(df_obj, "comm", None)
+    world, rank = sharding.world_info(comm)
     pcell = df_obj.cell
     kmesh = df_obj.kmesh
     vk = numpy.asarray(df_obj.kpts)
@@ -111,6 +119,7 @@ def build(df_obj):
     nkpt = int(numpy.prod(kmesh))
     stats = df_obj._stats = dict(h2d_bytes=0, d2h_bytes=0)
     ev = df_obj._events = {}
+    df_obj._host_cache = {}
 
     def mark(name):
         e = torch.cuda.Event(enable_timing=True)
@@ -148,16 +157,37 @@ def build(df_obj):
     if getattr(df_obj, "keep_metric", False):
         df_obj._a_q = a_q.clone()
 
-    # ---- C(a). rank-revealing Cholesky of every A_q (replaces the QRCP inside zgelsy, :108)
+    # ---- C(a). rank-revealing Cholesky of every A_q (replaces the QRCP inside zgelsy, :108);
+    #      q-slots are dealt round-robin to the ranks and the factors all-gathered.
     rcond = getattr(df_obj, "rcond", -1.0)
-    u_q, piv_q, rank_q, _ = ops.pchol(a_q, max_steps=nip, tol=rcond, nb=df_obj.chol_nb)
+    mine = sharding.slot_shard(nq, world, rank)
+    if mine:
+        a_mine = a_q[mine].contiguous() if world > 1 else a_q
+        u_q, piv_l, rank_l, _ = ops.pchol(a_mine, max_steps=nip, tol=rcond, nb=df_obj.chol_nb)
+        del a_mine
+    else:
+        u_q = None
+        piv_l = torch.zeros((0, nip), dtype=torch.int32, device=dev)
+        rank_l = torch.zeros((0,), dtype=torch.int32, device=dev)
     del a_q
-    nipP = -(-nip // TB) * TB
-    lfwd, ubwd = ops.trsm_prepare(u_q, piv_q, rank_q, nipP)
-    del u_q
+    piv_q = sharding.allgather_slots(piv_l, nq, comm)
+    rank_q = sharding.allgather_slots(rank_l, nq, comm)
     piv_h = piv_q.cpu().numpy()
     rank_h = rank_q.cpu().numpy()
     stats["d2h_bytes"] += piv_h.nbytes + rank_h.nbytes
+    # rows at positions >= max rank are identically zero from here on: drop them (multiple of 64 and of world)
+    nipP = max(TB, -(-int(rank_h.max()) // TB) * TB)
+    while nipP % world:
+        nipP += TB
+    if mine:
+        lf_l, ub_l = ops.trsm_prepare(u_q, piv_l, rank_l, nipP)
+    else:
+        lf_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
+        ub_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
+    del u_q
+    lfwd = sharding.allgather_slots(lf_l, nq, comm)
+    ubwd = sharding.allgather_slots(ub_l, nq, comm)
+    del lf_l, ub_l
     rowmap_h = -numpy.ones((nq, nip), dtype=numpy.int32)
     for s in range(nq):
         r = int(rank_h[s])
@@ -165,15 +195,26 @@ def build(df_obj):
     rowmap = torch.from_numpy(rowmap_h).to(dev)
     mark("metric")
 
-    # ---- B2. right-hand side Y_q^T, written straight into pivot order           :72-87
+    # ---- B2. right-hand side Y_q^T for this rank's grid columns, written straight into pivot order  :72-87
     grids = df_obj.grids
     coord = numpy.asarray(grids.coords)
     ngrid = coord.shape[0]
+    g_lo, g_hi, ncol = sharding.col_shard(ngrid, world, rank)
     _log(df_obj, "nkpt = %d, ngrid = %d, nip = %d", nkpt, ngrid, nip)
-    theta = torch.zeros((nq, nipP, ngrid), dtype=torch.complex128, device=dev)  # Y^T, then Theta, then B
+    theta = torch.zeros((nq, nipP, ncol), dtype=torch.complex128, device=dev)  # Y^T, then Theta, then B
     blksize = int(df_obj.blksize)
     fx_k = None
-    for ao_k_etc, g0, g1 in df_obj.aoR_loop(grids, vk, 0, blksize=blksize):   # :72
+    tab = getattr(df_obj, "_ao_tables", None)
+    if tab is not None and not torch.is_tensor(tab) and tab[:, g_lo:g_hi].nbytes <= df_obj.table_upload_limit:
+        # host AO table that fits: one pinned H2D copy of this rank's rows, blocks are then device views
+        part = tab if world == 1 else numpy.ascontiguousarray(tab[:, g_lo:g_hi])
+        stats["h2d_bytes"] += part.nbytes
+        df_obj._ao_tables_dev = (_to_dev(ops, part), g_lo)
+    elif torch.is_tensor(tab):
+        df_obj._ao_tables_dev = (tab, 0)
+    else:
+        df_obj._ao_tables_dev = None
+    for ao_k_etc, g0, g1 in df_obj.aoR_loop(grids, vk, 0, blksize=blksize, g_range=(g_lo, g_hi)):   # :72
         f_k = ao_k_etc[0]
         if not torch.is_tensor(f_k):
             f_k = numpy.asarray(f_k)                                          # :73
@@ -184,11 +225,12 @@ def build(df_obj):
         if fx_k is None or fx_k.shape[1] != blk:
             fx_k = torch.empty((nkpt, blk, nip), dtype=torch.complex128, device=dev)
         ops.gram_conja(f_k, xip, out=fx_k)                                    # :76
-        ops.ktransform_square(fx_k, blk * nip, nip, theta, nipP * ngrid, 1, ngrid, g0, blk, nip, kmesh, uax,
+        ops.ktransform_square(fx_k, blk * nip, nip, theta, nipP * ncol, 1, ncol, g0 - g_lo, blk, nip, kmesh, uax,
                               conj2=0, out_g_fast=1, qslot=qslot, rowmap=rowmap, rowmap_sq=nip,
                               diag=diag[2:4])                                 # :79-85
         _log(df_obj, "finished aoR_loop[%8d:%8d]", g0, g1)
     del fx_k
+    df_obj._ao_tables_dev = None
     mark("rhs")
 
     # ---- C(b). Theta_q = A_q^+ Y_q^T by two blocked triangular sweeps, all q at once  :108
@@ -196,20 +238,29 @@ def build(df_obj):
     del lfwd, ubwd
     mark("fit")
     if getattr(df_obj, "keep_theta", False):
-        df_obj._theta_dev = ops.gather_rows(theta[:, :nip, :].contiguous() if nipP != nip else theta, rowmap)
+        # original row order, this rank's grid columns [g_lo, g_hi)
+        df_obj._theta_dev = ops.gather_rows(theta, rowmap)[:, :, : g_hi - g_lo]
 
     # ---- D. Coulomb kernel                                                       :96-122
     vol = float(pcell.vol)
-    wq = torch.empty((nkpt, nip, nip), dtype=torch.complex128, device=dev)
-    wslot = torch.empty((nq, nip, nip), dtype=torch.complex128, device=dev)
+    vecs = sharding.to_vector_layout(theta, comm)            # [nq][nipP/world][world*ncol]
+    if world > 1:
+        del theta
+    nv, ldv = vecs.shape[1], vecs.shape[2]
     for s, q in enumerate(qind):                                              # :97
         vq = vk[q]
         fq = numpy.exp(-1j * numpy.dot(coord, vq))                            # :99
-        coulg = coulg_all[q]                                                  # :114
-        wgt = numpy.sqrt(coulg * vol) / ngrid                                 # :115 folded with Parseval's 1/ng
-        ops.fft3d(theta[s], mesh, pre=torch.from_numpy(fq).to(dev), post=torch.from_numpy(wgt).to(dev))  # :113-115
+        wgt = numpy.sqrt(coulg_all[q] * vol) / ngrid                          # :114-115 with Parseval's 1/ng
+        ops.fft3d(vecs[s], mesh, pre=torch.from_numpy(fq).to(dev), post=torch.from_numpy(wgt).to(dev),
+                  nvec=nv, ldv=ldv)                                           # :113-115
     mark("fft")
-    ops.herk_strided(theta, ngrid, nipP * ngrid, nip, ngrid, 1.0, piv_q, nip, wslot, nq)  # :121
+    theta = sharding.to_column_layout(vecs, comm)            # [nq][nipP][ncol]
+    del vecs
+    wslot = torch.zeros((nq, nip, nip), dtype=torch.complex128, device=dev)
+    nrow = min(nip, nipP)
+    ops.herk_strided(theta, ncol, nipP * ncol, nrow, ncol, 1.0, piv_q, nip, wslot, nip, nip * nip, nq)   # :121
+    sharding.allreduce_sum_(wslot, comm)
+    wq = torch.empty((nkpt, nip, nip), dtype=torch.complex128, device=dev)
     for s, q in enumerate(qind):
         wq[q].copy_(wslot[s])
         if partner[q] != q and tr_ok[q]:
@@ -221,22 +272,16 @@ def build(df_obj):
     assert d[0] < 1e-10 * max(1.0, d[1]) or d[0] < 1e-10, "abs(x2_s.imag).max() = %g" % d[0]   # :43
     assert d[2] < 1e-10 * max(1.0, d[3]) or d[2] < 1e-10, "abs(fx_s.imag).max() = %g" % d[2]   # :81
 
-    df_obj._x_dev = xip
-    df_obj._wq_dev = wq
+    df_obj._x_dev = xip                                                        # :125
+    df_obj._wq_dev = wq                                                        # :127-128
     df_obj._ranks = rank_h.copy()
     df_obj._qind = list(qind)
-    x_h = xip.cpu().numpy()
-    wq_h = wq.cpu().numpy()
-    stats["d2h_bytes"] += x_h.nbytes + wq_h.nbytes
     mark("end")
     torch.cuda.synchronize(dev)
     names = ["start", "select", "metric", "rhs", "fit", "fft", "kernel", "end"]
     df_obj._stage_ms = {names[i + 1]: ev[names[i]].elapsed_time(ev[names[i + 1]]) for i in range(len(names) - 1)}
     for s, q in enumerate(qind):
         _log(df_obj, "w[%3d], rank = %4d / %4d", q, int(rank_h[s]), nip)       # :122
-    df_obj._x = x_h                                                            # :125
-    df_obj._w0 = wq_h[0]                                                       # :127
-    df_obj._wq = wq_h                                                          # :128
 
 
 def get_j_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=None, exxdiv=None):
@@ -295,11 +340,41 @@ def get_k_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=Non
 
 
 class InterpolativeSeparableDensityFitting(_Base):
-    _x = None
-    _w0 = None
-    _wq = None
+    # _x, _w0, _wq (fftisdf.py:297-299) are numpy views of the device results, copied to pinned host
+    # memory on first access after build() (the device tensors stay in _x_dev / _wq_dev).
+    _x_dev = None
+    _wq_dev = None
+
+    def _host(self, name):
+        cache = self.__dict__.setdefault("_host_cache", {})
+        if name not in cache:
+            t = getattr(self, name + "_dev")
+            if t is None:
+                return None
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            cache[name] = buf.numpy()
+            if hasattr(self, "_stats"):
+                self._stats["d2h_bytes"] += cache[name].nbytes
+        return cache[name]
+
+    @property
+    def _x(self):
+        return self._host("_x")
+
+    @property
+    def _wq(self):
+        return self._host("_wq")
+
+    @property
+    def _w0(self):
+        w = self._host("_wq")
+        return None if w is None else w[0]
+
     blksize = 8000   # block size for the aoR_loop            (fftisdf.py:300)
     chol_nb = 32     # panel width of the pivoted Cholesky kernels
+    table_upload_limit = 48 * 2 ** 30  # host AO tables up to this size are uploaded in one copy
 
     def __init__(self, cell, kpts, m0=None, c0=20.0, device=0):
         super().__init__(cell, kpts)
@@ -316,7 +391,7 @@ class InterpolativeSeparableDensityFitting(_Base):
         _log(self, "transformed kmesh = %s", kmesh)
         return build(self)
 
-    def aoR_loop(self, grids=None, kpts=None, deriv=0, blksize=None):
+    def aoR_loop(self, grids=None, kpts=None, deriv=0, blksize=None, g_range=None):
         """fftisdf.py:327-355: yields (ao_k_etc, p0, p1); ao_k_etc[0] = per-k [blk, nao] AO values,
         ao_k_etc[4] = coords.  PySCF's NumInt.block_loop when available, else cell.pbc_eval_gto."""
         if grids is None:
@@ -336,15 +411,26 @@ class InterpolativeSeparableDensityFitting(_Base):
                                                      max_memory=max(2000, self.max_memory), blksize=blksize):
                 coords = ao_k1_etc[4]
                 p0, p1 = p1, p1 + coords.shape[0]
-                yield ao_k1_etc, p0, p1
+                if g_range is None:
+                    yield ao_k1_etc, p0, p1
+                else:  # clip the block to this rank's grid rows
+                    q0, q1 = max(p0, g_range[0]), min(p1, g_range[1])
+                    if q0 < q1:
+                        ao = numpy.asarray(ao_k1_etc[0])[:, q0 - p0:q1 - p0]
+                        yield (ao, ao, None, None, coords[q0 - p0:q1 - p0]), q0, q1
             return
         coords_all = numpy.asarray(grids.coords)
-        ao_all = getattr(self, "_ao_tables", None)
-        for p0 in range(0, len(coords_all), blksize):
-            p1 = min(len(coords_all), p0 + blksize)
+        lo, hi = (0, len(coords_all)) if g_range is None else g_range
+        dev_tab = getattr(self, "_ao_tables_dev", None)
+        host_tab = getattr(self, "_ao_tables", None)
+        for p0 in range(lo, hi, blksize):
+            p1 = min(hi, p0 + blksize)
             c = coords_all[p0:p1]
-            if ao_all is not None:
-                ao = ao_all[:, p0:p1, :]
+            if dev_tab is not None:
+                t, off = dev_tab
+                ao = t[:, p0 - off:p1 - off, :]
+            elif host_tab is not None:
+                ao = host_tab[:, p0:p1, :]
             else:
                 ao = numpy.asarray(cell.pbc_eval_gto("GTOval", c, kpts=kpts))
             yield (ao, ao, None, None, c), p0, p1
@@ -378,6 +464,9 @@ class InterpolativeSeparableDensityFitting(_Base):
         nmax = min(int(nao * c0), ng)
         u, piv, rank, nxt = ops.pchol(x4.reshape(1, ng, ng), max_steps=nmax, tol=-1.0, nb=self.chol_nb)  # :381-382
         del u, x4
+        comm = getattr(self, "comm", None)
+        sharding.broadcast_(piv, 0, comm)   # every rank must use the same points (bitwise)
+        sharding.broadcast_(rank, 0, comm)
         nip = int(rank.cpu()[0])                                                           # :383  min(int(nao*c0), rank)
         mask = piv[0, :nip].contiguous()                                                   # :384
         self._mask = mask.cpu().numpy().astype(numpy.int64)

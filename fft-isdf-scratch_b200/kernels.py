@@ -72,13 +72,16 @@ class IsdfOps:
 
     # ---- batched conj(A) B^T  (fftisdf.py:38, :76) -----------------------------------------
     def gram_conja(self, a, b, out=None):
-        _chk(a, c128), _chk(b, c128)
+        """out[z] = conj(a[z]) @ b[z]^T; a, b may be strided views with a unit-stride last axis."""
+        assert a.is_cuda and b.is_cuda and a.dtype == c128 and b.dtype == c128
+        assert a.stride(2) == 1 and b.stride(2) == 1
         batch, m, k = a.shape
         _, n, _ = b.shape
         if out is None:
             out = torch.empty((batch, m, n), dtype=c128, device=self.device)
-        self.handle.check(self.lib.isdf_gram_conja(self.h, _ptr(a), k, m * k, _ptr(b), k, n * k, _ptr(out), n, m * n,
-                                                   m, n, k, batch, _stream()), "isdf_gram_conja")
+        self.handle.check(self.lib.isdf_gram_conja(self.h, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1),
+                                                   b.stride(0), _ptr(out), n, m * n, m, n, k, batch, _stream()),
+                          "isdf_gram_conja")
         self.launches += 1
         return out
 
@@ -130,13 +133,17 @@ class IsdfOps:
         self.launches += 2 * (nP // TB)
 
     # ---- K6: batched 3-D FFT with fused phase / weight ----------------------------------------
-    def fft3d(self, data, mesh, pre=None, post=None, group_vecs=0):
-        _chk(data, c128)
-        nvec = data.numel() // int(np.prod(mesh))
-        m = (C.c_int * 3)(*[int(x) for x in mesh])
-        self.handle.check(self.lib.isdf_fft3d_batched(self.h, _ptr(data), nvec, m, _ptr(pre), _ptr(post),
-                                                      int(group_vecs), _stream()), "isdf_fft3d_batched")
+    def fft3d(self, data, mesh, pre=None, post=None, group_vecs=0, nvec=None, ldv=None):
+        """data: [..., ldv] rows of length prod(mesh) (row pitch ldv), transformed in place."""
+        assert data.is_cuda and data.dtype == c128 and data.stride(-1) == 1
         ng = int(np.prod(mesh))
+        if ldv is None:
+            ldv = ng
+        if nvec is None:
+            nvec = data.numel() // ldv
+        m = (C.c_int * 3)(*[int(x) for x in mesh])
+        self.handle.check(self.lib.isdf_fft3d_batched(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
+                                                      int(group_vecs), _stream()), "isdf_fft3d_batched")
         gv = group_vecs if group_vecs > 0 else max(1, int(48 * 1024 * 1024 / (ng * 16)))
         self.launches += 3 * (-(-nvec // gv))
 
@@ -152,9 +159,9 @@ class IsdfOps:
         self.launches += 1
         return out
 
-    def herk_strided(self, b_ptr_tensor, ldb, strideB, n, k, alpha, perm, stride_perm, out, batch):
-        self.handle.check(self.lib.isdf_herk_scatter(self.h, _ptr(b_ptr_tensor), ldb, strideB, n, k, float(alpha),
-                                                     _ptr(perm), stride_perm, _ptr(out), n, n * n, batch, _stream()),
+    def herk_strided(self, b, ldb, strideB, n, k, alpha, perm, stride_perm, out, ldw, strideW, batch):
+        self.handle.check(self.lib.isdf_herk_scatter(self.h, _ptr(b), ldb, strideB, n, k, float(alpha), _ptr(perm),
+                                                     stride_perm, _ptr(out), ldw, strideW, batch, _stream()),
                           "isdf_herk_scatter")
         self.launches += 1
 

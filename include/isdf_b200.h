@@ -67,7 +67,7 @@ int isdf_ktransform_square(void* handle, const void* in, long in_sk, long in_sg,
                            void* stream);
 
 /* fftisdf.py:108  scipy.linalg.lstsq(A_q, Y_q^T): block operators of the two triangular sweeps from the
- * pivoted factor (block size 64).  n = nip, nP = n rounded up to 64.  lfwd, ubwd [batch][nP][nP];
+ * pivoted factor (block size 64).  n = nip, nP = multiple of 64 >= max(rank) (usually n rounded up).  lfwd, ubwd [batch][nP][nP];
  * work 2*batch*nP*nP c128.  Rows/columns at positions >= rank are replaced by the identity. */
 int isdf_trsm_prepare(void* handle, const void* u, int ldu_rows, const int* piv, const int* rank, int n, int nP,
                       int batch, void* lfwd, void* ubwd, void* work, void* stream);
@@ -76,10 +76,10 @@ int isdf_trsm_sweeps(void* handle, const void* lfwd, const void* ubwd, void* t, 
                      void* stream);
 
 /* fftisdf.py:113-115  pbctools.fft(z_q * fq, mesh) * coulG * vol/ngrid  (the ifft at :118 is removed by
- * Parseval):  data [nvec][ng] in place, out[v][G] = post[G] * sum_r data[v][r] pre[r] e^{-iG.r}.
+ * Parseval):  data [nvec][ldv >= ng] in place, out[v][G] = post[G] * sum_r data[v][r] pre[r] e^{-iG.r}.
  * mesh[3] host; pre [ng] c128 or NULL; post [ng] f64 or NULL; group_vecs <= 0 picks an L2-sized group. */
-int isdf_fft3d_batched(void* handle, void* data, long nvec, const int* mesh, const void* pre, const double* post,
-                       long group_vecs, void* stream);
+int isdf_fft3d_batched(void* handle, void* data, long nvec, long ldv, const int* mesh, const void* pre,
+                       const double* post, long group_vecs, void* stream);
 int isdf_fft_release_plans(void* handle);
 
 /* fftisdf.py:121  W_q = zeta_q @ z_q^H  in Parseval form:

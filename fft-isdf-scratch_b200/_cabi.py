@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libisdf_b200.so")
+_LIB_PATH = os.environ.get("ISDF_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                         "libisdf_b200.so")  # env override: kernel-tuning builds only
 
 c_void_p, c_int, c_long, c_double, c_size_t = C.c_void_p, C.c_int, C.c_long, C.c_double, C.c_size_t
 P_int = C.POINTER(C.c_int)
@@ -41,6 +42,8 @@ SIGNATURES = {
                                c_int, P_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_long, c_void_p, c_void_p],
     "isdf_fft3d_batched": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_long, c_void_p],
     "isdf_fft_release_plans": [c_void_p],
+    "isdf_coulomb_weights": [c_void_p, C.POINTER(c_double), C.POINTER(c_double), P_int, c_double, c_void_p, c_void_p],
+    "isdf_phase_table": [c_void_p, c_void_p, C.POINTER(c_double), c_long, c_void_p, c_void_p],
 }
 
 

@@ -29,8 +29,14 @@ struct GemmParams {
   const int* active;                 // optional per-batch flag; batch skipped when 0
 };
 
-constexpr int GEMM_BK = 8;
-constexpr int GEMM_STAGES = 4;
+#ifndef ISDF_GEMM_BK
+#define ISDF_GEMM_BK 8
+#endif
+#ifndef ISDF_GEMM_STAGES
+#define ISDF_GEMM_STAGES 4
+#endif
+constexpr int GEMM_BK = ISDF_GEMM_BK;        // complex K elements per pipeline stage (multiple of 4)
+constexpr int GEMM_STAGES = ISDF_GEMM_STAGES;
 constexpr int GEMM_THREADS = 512;
 
 template <int BM, int BN, bool A_KSLOW, bool B_KSLOW>

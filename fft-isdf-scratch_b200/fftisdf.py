@@ -137,11 +137,11 @@ def build(df_obj):
     # ---- B1. metric A_q                                                        :38-48
     uax = ops.pack_uaxes(kmesh)
     mesh = [int(m) for m in df_obj.mesh]
-    gv = pcell.get_Gv(mesh)                                                   # :91
-    coulg_all = [pbc_tools.get_coulG(a, vq, mesh, Gv=gv) for vq in vk]       # :114 (O(nk*ng) host tables)
     partner = pbc_tools.time_reversal_partner(kmesh)
     use_tr = bool(getattr(df_obj, "use_time_reversal", True))
-    tr_ok = _time_reversal_valid(kmesh, mesh, coulg_all, partner) if use_tr else numpy.zeros(nkpt, bool)
+    # W_{-q} = conj(W_q) is exact for odd FFT meshes (what PySCF's cutoff_to_mesh produces); even
+    # meshes break it at the Nyquist planes (see _time_reversal_valid, checked in the tests)
+    tr_ok = numpy.array([use_tr and all(m % 2 == 1 for m in mesh) and partner[q] != q for q in range(nkpt)])
     qind = [q for q in range(nkpt) if not (tr_ok[q] and partner[q] < q)]
     nq = len(qind)
     qslot_h = -numpy.ones(nkpt, dtype=numpy.int32)
@@ -247,12 +247,16 @@ def build(df_obj):
     if world > 1:
         del theta
     nv, ldv = vecs.shape[1], vecs.shape[2]
+    coord_d = _to_dev(ops, coord, pinned=False)
+    stats["h2d_bytes"] += coord.nbytes
+    bvec = pbc_tools.reciprocal_vectors(a)
+    kscaled = pbc_tools.get_scaled_kpts(a, vk)
+    fq_d = torch.empty((ngrid,), dtype=torch.complex128, device=dev)
+    wgt_d = torch.empty((ngrid,), dtype=torch.float64, device=dev)
     for s, q in enumerate(qind):                                              # :97
-        vq = vk[q]
-        fq = numpy.exp(-1j * numpy.dot(coord, vq))                            # :99
-        wgt = numpy.sqrt(coulg_all[q] * vol) / ngrid                          # :114-115 with Parseval's 1/ng
-        ops.fft3d(vecs[s], mesh, pre=torch.from_numpy(fq).to(dev), post=torch.from_numpy(wgt).to(dev),
-                  nvec=nv, ldv=ldv)                                           # :113-115
+        ops.phase_table(coord_d, vk[q], fq_d)                                 # :99   fq = exp(-i r.q)
+        ops.coulomb_weights(bvec, kscaled[q], mesh, vol, wgt_d)               # :114-115 sqrt(coulG vol)/ng
+        ops.fft3d(vecs[s], mesh, pre=fq_d, post=wgt_d, nvec=nv, ldv=ldv)      # :113-115
     mark("fft")
     theta = sharding.to_column_layout(vecs, comm)            # [nq][nipP][ncol]
     del vecs
@@ -275,6 +279,7 @@ def build(df_obj):
     df_obj._x_dev = xip                                                        # :125
     df_obj._wq_dev = wq                                                        # :127-128
     df_obj._ranks = rank_h.copy()
+    df_obj._nipP = nipP
     df_obj._qind = list(qind)
     mark("end")
     torch.cuda.synchronize(dev)

@@ -165,6 +165,21 @@ class IsdfOps:
                           "isdf_herk_scatter")
         self.launches += 1
 
+    # ---- device-side per-q tables (fftisdf.py:99, :114-115) -----------------------------------
+    def coulomb_weights(self, b, kscaled, mesh, vol, out):
+        bb = (C.c_double * 9)(*[float(x) for x in np.asarray(b).reshape(9)])
+        ks = (C.c_double * 3)(*[float(x) for x in kscaled])
+        m = (C.c_int * 3)(*[int(x) for x in mesh])
+        self.handle.check(self.lib.isdf_coulomb_weights(self.h, bb, ks, m, float(vol), _ptr(out), _stream()),
+                          "isdf_coulomb_weights")
+        self.launches += 1
+
+    def phase_table(self, coords_dev, q, out):
+        qq = (C.c_double * 3)(*[float(x) for x in q])
+        self.handle.check(self.lib.isdf_phase_table(self.h, _ptr(coords_dev), qq, coords_dev.shape[0], _ptr(out),
+                                                    _stream()), "isdf_phase_table")
+        self.launches += 1
+
     def conj_copy(self, src, dst):
         self.handle.check(self.lib.isdf_conj_copy(self.h, _ptr(src), _ptr(dst), src.numel(), _stream()),
                           "isdf_conj_copy")

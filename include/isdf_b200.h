@@ -82,6 +82,15 @@ int isdf_fft3d_batched(void* handle, void* data, long nvec, long ldv, const int*
                        const double* post, long group_vecs, void* stream);
 int isdf_fft_release_plans(void* handle);
 
+/* Per-q tables of the Coulomb stage generated on the device:
+ * fftisdf.py:114-115  get_coulG(cell, k=vq, mesh) (exxdiv=None, wrap_around=True) folded with vol/ngrid and
+ * Parseval's 1/ngrid:  out[G] = sqrt(v(q+G) vol)/ng.  b [3][3] reciprocal vectors (rows) and kscaled [3]
+ * (q in units of b) are HOST pointers; out is a device pointer.
+ * fftisdf.py:99  fq = exp(-i coords . vq):  coords [ng][3] device, q [3] host (cartesian). */
+int isdf_coulomb_weights(void* handle, const double* b_host, const double* kscaled_host, const int* mesh, double vol,
+                         double* out, void* stream);
+int isdf_phase_table(void* handle, const double* coords, const double* q_host, long ng, void* out, void* stream);
+
 /* fftisdf.py:121  W_q = zeta_q @ z_q^H  in Parseval form:
  * w[z][perm[i]][perm[j]] = alpha * sum_g b[z][i][g] conj(b[z][j][g]);  exactly Hermitian output.
  * perm [batch][stridePerm...] position -> original index, or NULL. */

@@ -228,3 +228,29 @@ def test_gather_and_conj(ops):
     d = torch.empty_like(s)
     ops.conj_copy(s, d)
     assert np.array_equal(d.cpu().numpy(), src.conj())
+
+
+@pytest.mark.parametrize("mesh,kmesh", [([9, 11, 7], [2, 3, 1]), ([8, 9, 10], [3, 2, 1]), ([12, 12, 12], [2, 2, 2]),
+                                        ([15, 15, 15], [4, 4, 4])])
+def test_device_coulomb_weights_and_phase(ops, mesh, kmesh):
+    """Device tables == host restatement of pbctools.get_coulG (wrap-around, boundary zeroing) and exp(-iq.r)."""
+    import fft_isdf_scratch_b200 as pk
+    T = pk.pbc_tools
+    a = np.array([[6.1, 0.9, 0.0], [0.0, 5.3, -0.7], [0.5, 0.0, 7.2]])
+    kpts = T.make_kpts(a, kmesh)
+    ks = T.get_scaled_kpts(a, kpts)
+    b = T.reciprocal_vectors(a)
+    ng = int(np.prod(mesh))
+    vol = abs(np.linalg.det(a))
+    coords = T.gen_uniform_grids(a, mesh)
+    cd = dev(coords)
+    w = torch.empty(ng, dtype=torch.float64, device="cuda")
+    f = torch.empty(ng, dtype=torch.complex128, device="cuda")
+    for q in range(len(kpts)):
+        ops.coulomb_weights(b, ks[q], mesh, vol, w)
+        ref = np.sqrt(T.get_coulG(a, kpts[q], mesh) * vol) / ng
+        got = w.cpu().numpy()
+        assert np.array_equal(got == 0.0, ref == 0.0)          # same zeroed entries (G=0, box boundary)
+        assert relerr(got, ref) < 1e-13
+        ops.phase_table(cd, kpts[q], f)
+        assert relerr(f.cpu().numpy(), np.exp(-1j * coords @ kpts[q])) < 1e-13

@@ -133,3 +133,25 @@ def test_no_cpu_fallback_without_gpu():
     cell = pk.random_cubic_cell(8, 3, seed=0, L=6.0)
     with pytest.raises(Exception):
         fftisdf.ISDF(cell, cell.get_kpts([1, 1, 1]))
+
+
+def test_time_reversal_rule_odd_mesh():
+    """build() exploits W_{-q} = W_q^* iff every FFT mesh dimension is odd; check that rule against the
+    numeric criterion on the Coulomb tables for several lattices / meshes / k-meshes."""
+    import fft_isdf_scratch_b200 as pk
+    from fft_isdf_scratch_b200.fftisdf import _time_reversal_valid
+    T = pk.pbc_tools
+    rng = np.random.default_rng(3)
+    for mesh, kmesh in [([9, 11, 7], [2, 3, 1]), ([15, 15, 15], [4, 4, 4]), ([7, 7, 9], [3, 3, 3]), ([5, 9, 11], [5, 2, 4]),
+                        ([37, 37, 37], [3, 3, 3])]:
+        a = np.eye(3) * 6.0 + rng.uniform(-1, 1, (3, 3))
+        kp = T.make_kpts(a, kmesh)
+        part = T.time_reversal_partner(kmesh)
+        cg = [T.get_coulG(a, k, mesh) for k in kp]
+        ok = _time_reversal_valid(kmesh, mesh, cg, part)
+        assert all(ok[q] for q in range(len(kp)) if part[q] != q), (mesh, kmesh)
+    a = np.eye(3) * 6.0 + rng.uniform(-1, 1, (3, 3))
+    kp = T.make_kpts(a, [3, 2, 1])
+    cg = [T.get_coulG(a, k, [8, 9, 10]) for k in kp]
+    ok = _time_reversal_valid([3, 2, 1], [8, 9, 10], cg, T.time_reversal_partner([3, 2, 1]))
+    assert not ok.any()

@@ -17,8 +17,10 @@
 
 namespace isdf {
 
-constexpr int FFT_THREADS = 256;
+constexpr int FFT_THREADS = 128;
 constexpr int FFT_MAXSTAGES = 8;
+constexpr int FFT_OB = 4;   // outputs per thread (register blocking)
+constexpr int FFT_LB = 4;   // lines per thread
 
 struct FftParams {
   cplx* data;        // in place
@@ -41,7 +43,7 @@ struct FftParams {
 __global__ void __launch_bounds__(FFT_THREADS) fft_lines_kernel(FftParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = p.n, T = p.T;
-  const int Tp = T | 1;  // odd pitch (in 16-byte units): conflict-free for both access orders
+  const int Tp = (T + FFT_LB) | 1;  // odd pitch (16-byte units), with room for the masked tail lines of a block
   cplx* X = reinterpret_cast<cplx*>(smem_raw);
   cplx* Y = X + (long)n * Tp;
   cplx* W = Y + (long)n * Tp;
@@ -88,26 +90,63 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_lines_kernel(FftParams p) {
     const int R = p.radix[st];
     const int m = ncur / R;
     const int nR = n / R;
-    const int tot = n * lcnt;
+    // Register-blocked direct R-point DFT: a work item = (butterfly, chunk of FFT_OB outputs, FFT_LB lines).
+    // Every x load is reused for FFT_OB outputs and every twiddle load for FFT_LB lines, which moves the
+    // kernel from shared-memory-bandwidth bound (2 LDS per complex MAC) to the FP64 pipe (0.5 LDS/MAC).
+    const int nbf = n / R;                       // butterflies per line
+    const int nch = (R + FFT_OB - 1) / FFT_OB;   // output chunks per butterfly
+    const int nlb = (lcnt + FFT_LB - 1) / FFT_LB;
+    const int tot = nbf * nch * nlb;
+    const long xstep = (long)s * m * Tp;
     for (int w = threadIdx.x; w < tot; w += FFT_THREADS) {
-      const int o = w / lcnt, l = w - o * lcnt;   // output index o = q + s*(R*pp + r1)
-      const int q = o % s;
-      const int tmp = o / s;
-      const int r1 = tmp % R;
-      const int pp = tmp / R;
-      // y[o] = w_ncur^{pp*r1} * sum_r x[q + s*(pp + m*r)] * w_R^{r*r1}
-      const int step = (int)(((long)nR * r1) % n);   // index step of w_R^{r1} per r
-      int widx = 0;
-      cplx acc = make_double2(0.0, 0.0);
-      const cplx* xin = src + (long)(q + s * pp) * Tp + l;
-      const long xstep = (long)s * m * Tp;
-      for (int r = 0; r < R; ++r) {
-        cfma(acc, xin[r * xstep], W[widx]);
-        widx += step;
-        if (widx >= n) widx -= n;
+      const int lb = w % nlb;
+      const int tmp = w / nlb;
+      const int ch = tmp % nch;
+      const int bf = tmp / nch;
+      const int pp = bf / s, q = bf - pp * s;
+      const int r10 = ch * FFT_OB;
+      int step[FFT_OB], widx[FFT_OB];
+#pragma unroll
+      for (int j = 0; j < FFT_OB; ++j) {
+        const int r1 = min(r10 + j, R - 1);
+        step[j] = (int)(((long)nR * r1) % n);    // index step of w_R^{r1} per input r
+        widx[j] = 0;
       }
-      const int tidx = (int)(((long)pp * r1 % n) * s % n);
-      dst[(long)o * Tp + l] = cmul(acc, W[tidx]);
+      cplx acc[FFT_OB][FFT_LB];
+#pragma unroll
+      for (int j = 0; j < FFT_OB; ++j)
+#pragma unroll
+        for (int l = 0; l < FFT_LB; ++l) acc[j][l] = make_double2(0.0, 0.0);
+      const cplx* xin = src + (long)(q + s * pp) * Tp + lb;
+      for (int r = 0; r < R; ++r) {
+        cplx xs[FFT_LB], ws[FFT_OB];
+#pragma unroll
+        for (int l = 0; l < FFT_LB; ++l) xs[l] = xin[r * xstep + l * nlb];   // lines lb + l*nlb (pad lines are zero-safe)
+#pragma unroll
+        for (int j = 0; j < FFT_OB; ++j) {
+          ws[j] = W[widx[j]];
+          widx[j] += step[j];
+          if (widx[j] >= n) widx[j] -= n;
+        }
+#pragma unroll
+        for (int j = 0; j < FFT_OB; ++j)
+#pragma unroll
+          for (int l = 0; l < FFT_LB; ++l) cfma(acc[j][l], xs[l], ws[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < FFT_OB; ++j) {
+        const int r1 = r10 + j;
+        if (r1 < R) {
+          const int tidx = (int)(((long)pp * r1 % n) * s % n);
+          const cplx tw = W[tidx];
+          const int o = q + s * (R * pp + r1);
+#pragma unroll
+          for (int l = 0; l < FFT_LB; ++l) {
+            const int line = lb + l * nlb;
+            if (line < lcnt) dst[(long)o * Tp + line] = cmul(acc[j][l], tw);
+          }
+        }
+      }
     }
     __syncthreads();
     cplx* tswap = src; src = dst; dst = tswap;
@@ -206,8 +245,8 @@ static int launch_pass(Handle* h, cplx* data, long nvec, long ldv, int n, long s
   p.nstages = pl->nstages;
   for (int i = 0; i < FFT_MAXSTAGES; ++i) p.radix[i] = (i < pl->nstages) ? pl->radix[i] : 1;
   p.tw = pl->tw; p.pre = pre; p.post = post;
-  int T = 16;
-  auto bytes = [&](int t) { return ((size_t)2 * n * (t | 1) + n) * sizeof(cplx); };
+  int T = 32;
+  auto bytes = [&](int t) { return ((size_t)2 * n * ((t + FFT_LB) | 1) + n) * sizeof(cplx); };
   while (T > 1 && bytes(T) > (size_t)96 * 1024) T >>= 1;
   if (bytes(T) > (size_t)h->max_smem_optin) { snprintf(h->err, sizeof(h->err), "fft length %d too large", n); return ISDF_ESIZE; }
   if (T > lines_per_run) { T = 1; while (T * 2 <= lines_per_run) T *= 2; }

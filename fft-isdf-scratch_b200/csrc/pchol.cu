@@ -57,18 +57,19 @@ pchol_panel_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n,
   __shared__ double w_v;
   __shared__ int w_pos, w_idx;
 
+  extern __shared__ double s_aii[];  // [n] diagonal at panel start (dpstrf: work(n+i) = a_ii - work(i))
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double aii[PC_NCOL], ssum[PC_NCOL];
+  double ssum[PC_NCOL];
   int mypos[PC_NCOL];
 #pragma unroll
   for (int c = 0; c < PC_NCOL; ++c) {
     const int i = tid + c * PC_THREADS;
+    ssum[c] = 0.0;
     if (i < n) {
-      aii[c] = A[(long)i * lda + i].x;
-      ssum[c] = 0.0;
+      s_aii[i] = A[(long)i * lda + i].x;
       mypos[c] = pos[i];
     } else {
-      aii[c] = 0.0; ssum[c] = 0.0; mypos[c] = -1;
+      mypos[c] = -1;
     }
   }
   double dstop = info->dstop;
@@ -84,7 +85,7 @@ pchol_panel_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n,
 #pragma unroll
     for (int c = 0; c < PC_NCOL; ++c) {
       if (mypos[c] >= j) {
-        const double d = aii[c] - ssum[c];
+        const double d = s_aii[tid + c * PC_THREADS] - ssum[c];
         if (d > bv || (d == bv && mypos[c] < bpos)) { bv = d; bpos = mypos[c]; bidx = tid + c * PC_THREADS; }
       }
     }
@@ -132,32 +133,50 @@ pchol_panel_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n,
     // ---- 4. broadcast the pivot column's in-panel entries u_{t',p}
     if (tid < t) bp[tid] = __ldcg(&U[(long)(j0 + tid) * ldu + p]);
     __syncthreads();
-    // ---- 5. new row of U, residual update
+    // ---- 5. new row of U, residual update.  The t-loop is outermost so that the PC_NCOL independent
+    //         column updates of a thread overlap their U loads (latency-bound otherwise).
     const double rt = sqrt(dp);
     const double inv = 1.0 / rt;
     const cplx* Arow = A + (long)p * lda;
 #pragma unroll
-    for (int c = 0; c < PC_NCOL; ++c) {
-      const int i = tid + c * PC_THREADS;
-      if (i < n) {
-        cplx u;
-        if (i == p) {
-          u = make_double2(rt, 0.0);
-        } else if (mypos[c] > j) {
-          cplx v = Arow[i];
-          for (int tt = 0; tt < t; ++tt) {
-            const cplx ui = U[(long)(j0 + tt) * ldu + i];
-            const cplx bb = bp[tt];
+    for (int c0 = 0; c0 < PC_NCOL; c0 += 4) {
+      if (tid + c0 * PC_THREADS >= n) break;
+      cplx v[4];
+      bool act[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = tid + (c0 + c) * PC_THREADS;
+        act[c] = (i < n) && (i != p) && (mypos[c0 + c] > j);
+        v[c] = act[c] ? Arow[i] : make_double2(0.0, 0.0);
+      }
+      for (int tt = 0; tt < t; ++tt) {
+        const cplx bb = bp[tt];
+        const cplx* Urow = U + (long)(j0 + tt) * ldu + tid + c0 * PC_THREADS;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (act[c]) {
+            const cplx ui = Urow[c * PC_THREADS];
             // v -= conj(bb) * ui
-            v.x -= bb.x * ui.x + bb.y * ui.y;
-            v.y -= bb.x * ui.y - bb.y * ui.x;
+            v[c].x -= bb.x * ui.x + bb.y * ui.y;
+            v[c].y -= bb.x * ui.y - bb.y * ui.x;
           }
-          u = make_double2(v.x * inv, v.y * inv);
-          ssum[c] += u.x * u.x + u.y * u.y;
-        } else {
-          u = make_double2(0.0, 0.0);
         }
-        U[(long)j * ldu + i] = u;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = tid + (c0 + c) * PC_THREADS;
+        if (i < n) {
+          cplx u;
+          if (i == p) {
+            u = make_double2(rt, 0.0);
+          } else if (act[c]) {
+            u = make_double2(v[c].x * inv, v[c].y * inv);
+            ssum[c0 + c] += u.x * u.x + u.y * u.y;
+          } else {
+            u = make_double2(0.0, 0.0);
+          }
+          U[(long)j * ldu + i] = u;
+        }
       }
     }
     steps_done = t + 1;
@@ -346,9 +365,11 @@ extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, do
     ISDF_LAUNCH_CHECK(h);
   }
   const long strideA = (long)n * n, strideU = (long)ldu_rows * n;
+  ISDF_CUDA(h, cudaFuncSetAttribute(pchol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    PC_THREADS * PC_NCOL * (int)sizeof(double)));
   // The panel that reaches max_steps also evaluates the would-be next pivot and sets the stop flag.
   for (int j0 = 0; j0 == 0 || j0 < max_steps; j0 += nb) {
-    pchol_panel_kernel<<<batch, PC_THREADS, 0, st>>>((const cplx*)a, n, strideA, n, j0, nb, max_steps, tol, (cplx*)u, n,
+    pchol_panel_kernel<<<batch, PC_THREADS, (size_t)n * sizeof(double), st>>>((const cplx*)a, n, strideA, n, j0, nb, max_steps, tol, (cplx*)u, n,
                                                      strideU, pos, info, active);
     ISDF_LAUNCH_CHECK(h);
     if (j0 + nb < max_steps) {

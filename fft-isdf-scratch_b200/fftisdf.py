@@ -67,11 +67,22 @@ def _log(df_obj, msg, *args):
 
 
 def _to_dev(ops, arr, pinned=True):
-    """Host numpy -> device tensor through a pinned staging buffer (counted in df_obj._h2d_bytes)."""
+    """Host numpy -> device tensor (async from pinned memory when the source is pinned)."""
     t = torch.from_numpy(numpy.ascontiguousarray(arr))
-    if pinned:
+    if pinned and not t.is_pinned() and t.numel() * t.element_size() < (1 << 26):
         t = t.pin_memory()
     return t.to(ops.device, non_blocking=True)
+
+
+def _rows_to_dev(ops, tab, lo, hi):
+    """Device copy of tab[:, lo:hi, :] (host [nk, ng, nao]) without host staging: one async copy per k,
+    each source slice being contiguous in (ideally pinned) host memory."""
+    nk, _, nao = tab.shape
+    out = torch.empty((nk, hi - lo, nao), dtype=torch.complex128, device=ops.device)
+    src = torch.from_numpy(tab)
+    for k in range(nk):
+        out[k].copy_(src[k, lo:hi], non_blocking=True)
+    return out
 
 
 def _time_reversal_valid(kmesh, mesh, coulg_all, partner):
@@ -207,9 +218,8 @@ def build(df_obj):
     tab = getattr(df_obj, "_ao_tables", None)
     if tab is not None and not torch.is_tensor(tab) and tab[:, g_lo:g_hi].nbytes <= df_obj.table_upload_limit:
         # host AO table that fits: one pinned H2D copy of this rank's rows, blocks are then device views
-        part = tab if world == 1 else numpy.ascontiguousarray(tab[:, g_lo:g_hi])
-        stats["h2d_bytes"] += part.nbytes
-        df_obj._ao_tables_dev = (_to_dev(ops, part), g_lo)
+        stats["h2d_bytes"] += tab[:, g_lo:g_hi].nbytes
+        df_obj._ao_tables_dev = (_rows_to_dev(ops, tab, g_lo, g_hi), g_lo)
     elif torch.is_tensor(tab):
         df_obj._ao_tables_dev = (tab, 0)
     else:
@@ -356,7 +366,10 @@ class InterpolativeSeparableDensityFitting(_Base):
             t = getattr(self, name + "_dev")
             if t is None:
                 return None
-            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            pool = self.__dict__.setdefault("_pinned_pool", {})
+            buf = pool.get(name)
+            if buf is None or buf.shape != t.shape:
+                buf = pool[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             buf.copy_(t, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             cache[name] = buf.numpy()

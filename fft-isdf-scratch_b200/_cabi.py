@@ -25,6 +25,10 @@ SIGNATURES = {
     "isdf_select_gram": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "isdf_gram_conja": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_long, c_long,
                         c_int, c_int, c_int, c_int, c_void_p],
+    "isdf_gram_conjb": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_long, c_long,
+                        c_int, c_int, c_int, c_int, c_void_p],
+    "isdf_ktransform_square_rows": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_long, c_int, c_int,
+                                    P_int, c_void_p, c_int, c_void_p, c_void_p, c_long, c_void_p, c_void_p],
     "isdf_herk_scatter": [c_void_p, c_void_p, c_long, c_long, c_int, c_int, c_double, c_void_p, c_long, c_void_p,
                           c_long, c_long, c_int, c_void_p],
     "isdf_gemm_nn": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_long, c_long,

@@ -1,0 +1,148 @@
+// Register-resident variant of the k<->R transform / square / k<->R transform for small k-meshes
+// (nk <= 32, every axis <= 4): one thread owns all nk values of one element, so there is no shared
+// memory, no barrier and the input/output accesses are plain coalesced streams.  Same arithmetic and
+// reference lines as ktransform.cu (fftisdf.py:41-47, :79-85).  Input is [nk][rows][cols] with cols
+// contiguous; for the right-hand side the GEMM already produces the transposed fx^T[k][i][g], so the
+// output Y^T[q][row(i)][g] needs no transpose either.
+#include "common.cuh"
+
+namespace isdf {
+
+__constant__ cplx c_uax[3][8][8];  // U_a[m][j], a = 0,1,2 (pitch 8, as packed by the host)
+
+struct KtRegParams {
+  const cplx* in; long in_sk; long in_sr;      // in[k*in_sk + r*in_sr + c]
+  cplx* out; long out_sq; long out_sr; long out_c0;  // out[slot*out_sq + row*out_sr + out_c0 + c]
+  int nrows, ncols;
+  int conj2;
+  const int* qslot;                  // [nk] or null
+  const int* rowmap; long rowmap_sq; // [nslot][nrows] or null
+  double* diag;
+};
+
+template <int N, int STRIDE, int NK, int AX, bool CONJ>
+__device__ __forceinline__ void dft_axis(cplx (&x)[NK]) {
+  if constexpr (N > 1) {
+#pragma unroll
+  for (int base = 0; base < NK; ++base) {
+    // lines start where the axis index is 0:  (base / STRIDE) % N == 0
+    if ((base / STRIDE) % N != 0) continue;
+    cplx t[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) t[j] = x[base + j * STRIDE];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        cplx u = c_uax[AX][m][j];
+        if (CONJ) u.y = -u.y;
+        cfma(acc, u, t[j]);
+      }
+      x[base + m * STRIDE] = acc;
+    }
+  }
+  }
+}
+
+template <int N1, int N2, int N3>
+__global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
+  constexpr int NK = N1 * N2 * N3;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int r = blockIdx.y;
+  double mx_im = 0.0, mx_re = 0.0;
+  if (c < p.ncols) {
+    cplx x[NK];
+    const cplx* src = p.in + (long)r * p.in_sr + c;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) x[k] = src[(long)k * p.in_sk];
+    dft_axis<N3, 1, NK, 2, false>(x);
+    dft_axis<N2, N3, NK, 1, false>(x);
+    dft_axis<N1, N2 * N3, NK, 0, false>(x);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      mx_im = fmax(mx_im, fabs(x[k].y));
+      mx_re = fmax(mx_re, fabs(x[k].x));
+      x[k] = make_double2(x[k].x * x[k].x, 0.0);
+    }
+    if (p.conj2) {
+      dft_axis<N3, 1, NK, 2, true>(x);
+      dft_axis<N2, N3, NK, 1, true>(x);
+      dft_axis<N1, N2 * N3, NK, 0, true>(x);
+    } else {
+      dft_axis<N3, 1, NK, 2, false>(x);
+      dft_axis<N2, N3, NK, 1, false>(x);
+      dft_axis<N1, N2 * N3, NK, 0, false>(x);
+    }
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+      const int slot = p.qslot ? p.qslot[q] : q;
+      if (slot < 0) continue;
+      int row = r;
+      if (p.rowmap) {
+        row = p.rowmap[(long)slot * p.rowmap_sq + r];
+        if (row < 0) continue;
+      }
+      p.out[(long)slot * p.out_sq + (long)row * p.out_sr + p.out_c0 + c] = x[q];
+    }
+  }
+  if (p.diag != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx_im = fmax(mx_im, __shfl_xor_sync(0xffffffffu, mx_im, o));
+      mx_re = fmax(mx_re, __shfl_xor_sync(0xffffffffu, mx_re, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomic_max_nonneg(p.diag + 0, mx_im);
+      atomic_max_nonneg(p.diag + 1, mx_re);
+    }
+  }
+}
+
+template <int N1, int N2, int N3>
+static cudaError_t launch_reg(const KtRegParams& p, cudaStream_t st) {
+  dim3 grid((p.ncols + 127) / 128, p.nrows);
+  ktransform_reg_kernel<N1, N2, N3><<<grid, 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace isdf
+
+using namespace isdf;
+
+#define KT_CASE(a, b, c) \
+  if (n1 == a && n2 == b && n3 == c) { e = launch_reg<a, b, c>(p, st); hit = true; }
+
+// Returns ISDF_ESIZE (-2) without launching when the mesh has no register instantiation; the caller
+// then uses isdf_ktransform_square (shared-memory kernel).
+extern "C" int isdf_ktransform_square_rows(void* hv, const void* in, long in_sk, long in_sr, void* out, long out_sq,
+                                           long out_sr, long out_c0, int nrows, int ncols, const int* kmesh,
+                                           const void* uaxes_host, int conj2, const int* qslot, const int* rowmap,
+                                           long rowmap_sq, double* diag, void* stream) {
+  Handle* h = (Handle*)hv;
+  cudaStream_t st = (cudaStream_t)stream;
+  ISDF_CHECK_ARG(h, in && out && kmesh && uaxes_host, "null pointer");
+  const int n1 = kmesh[0], n2 = kmesh[1], n3 = kmesh[2];
+  ISDF_CHECK_ARG(h, n1 >= 1 && n2 >= 1 && n3 >= 1, "kmesh");
+  if (n1 > 4 || n2 > 4 || n3 > 4 || n1 * n2 * n3 > 32) return ISDF_ESIZE;
+  ISDF_CHECK_ARG(h, nrows <= 65535, "too many rows for one launch");
+  if (nrows <= 0 || ncols <= 0) return ISDF_OK;
+  ISDF_CUDA(h, cudaMemcpyToSymbolAsync(c_uax, uaxes_host, sizeof(cplx) * 3 * 64, 0, cudaMemcpyHostToDevice, st));
+  KtRegParams p;
+  p.in = (const cplx*)in; p.in_sk = in_sk; p.in_sr = in_sr;
+  p.out = (cplx*)out; p.out_sq = out_sq; p.out_sr = out_sr; p.out_c0 = out_c0;
+  p.nrows = nrows; p.ncols = ncols; p.conj2 = conj2;
+  p.qslot = qslot; p.rowmap = rowmap; p.rowmap_sq = rowmap_sq; p.diag = diag;
+  cudaError_t e = cudaSuccess;
+  bool hit = false;
+  KT_CASE(1, 1, 1) KT_CASE(1, 1, 2) KT_CASE(1, 2, 1) KT_CASE(2, 1, 1) KT_CASE(1, 2, 2) KT_CASE(2, 1, 2)
+  KT_CASE(2, 2, 1) KT_CASE(2, 2, 2) KT_CASE(1, 1, 3) KT_CASE(1, 3, 1) KT_CASE(3, 1, 1) KT_CASE(1, 3, 3)
+  KT_CASE(3, 1, 3) KT_CASE(3, 3, 1) KT_CASE(3, 3, 3) KT_CASE(2, 2, 3) KT_CASE(2, 3, 2) KT_CASE(3, 2, 2)
+  KT_CASE(2, 3, 3) KT_CASE(3, 2, 3) KT_CASE(3, 3, 2) KT_CASE(1, 2, 3) KT_CASE(1, 3, 2) KT_CASE(2, 1, 3)
+  KT_CASE(2, 3, 1) KT_CASE(3, 1, 2) KT_CASE(3, 2, 1) KT_CASE(1, 1, 4) KT_CASE(1, 4, 1) KT_CASE(4, 1, 1)
+  KT_CASE(2, 2, 4) KT_CASE(2, 4, 2) KT_CASE(4, 2, 2) KT_CASE(1, 4, 4) KT_CASE(4, 1, 4) KT_CASE(4, 4, 1)
+  KT_CASE(2, 4, 4) KT_CASE(4, 2, 4) KT_CASE(4, 4, 2)
+  if (!hit) return ISDF_ESIZE;
+  ISDF_CUDA(h, e);
+  return ISDF_OK;
+}

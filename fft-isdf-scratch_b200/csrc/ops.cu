@@ -99,6 +99,24 @@ extern "C" int isdf_gram_conja(void* hv, const void* a, long lda, long strideA, 
   return ISDF_OK;
 }
 
+// c[z][i][j] = sum_l a[z][i][l] * conj(b[z][j][l])      (fx_k^T = X_k F_k^H: the transposed form of fftisdf.py:76)
+extern "C" int isdf_gram_conjb(void* hv, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                               void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, a && b && c, "null pointer");
+  ISDF_CHECK_ARG(h, m >= 0 && n >= 0 && k >= 0 && batch >= 0 && batch <= 65535, "shape");
+  ISDF_CHECK_ARG(h, (m + 127) / 128 <= 65535, "m too large for one launch");
+  GemmParams p;
+  p.A = (const cplx*)a; p.lda = lda; p.strideA = strideA;
+  p.B = (const cplx*)b; p.ldb = ldb; p.strideB = strideB;
+  p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
+  p.M = m; p.N = n; p.K = k;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
 // w[z][perm[i]][perm[j]] = alpha * sum_g b[z][i][g] conj(b[z][j][g])   (Hermitian; lower tiles + mirror)
 // fftisdf.py:121 in Parseval form: W_q = B B^H.
 extern "C" int isdf_herk_scatter(void* hv, const void* b, long ldb, long strideB, int n, int k, double alpha,

@@ -160,10 +160,14 @@ def build(df_obj):
     qslot = torch.from_numpy(qslot_h).to(dev)
     diag = torch.zeros(4, dtype=torch.float64, device=dev)
 
+    uax_h = ops.pack_uaxes_host(kmesh)
     x2_k = ops.gram_conja(xip, xip)                                          # :38
     a_q = torch.empty((nq, nip, nip), dtype=torch.complex128, device=dev)
-    ops.ktransform_square(x2_k, nip * nip, nip, a_q, nip * nip, nip, 1, 0, nip, nip, kmesh, uax,
-                          conj2=1, out_g_fast=0, qslot=qslot, diag=diag[0:2])  # :41-47
+    reg_path = ops.ktransform_rows(x2_k, nip * nip, nip, a_q, nip * nip, nip, 0, nip, nip, kmesh, uax_h,
+                                   conj2=1, qslot=qslot, diag=diag[0:2])       # :41-47 (small k-mesh: registers)
+    if not reg_path:
+        ops.ktransform_square(x2_k, nip * nip, nip, a_q, nip * nip, nip, 1, 0, nip, nip, kmesh, uax,
+                              conj2=1, out_g_fast=0, qslot=qslot, diag=diag[0:2])  # :41-47
     del x2_k
     if getattr(df_obj, "keep_metric", False):
         df_obj._a_q = a_q.clone()
@@ -232,12 +236,20 @@ def build(df_obj):
             stats["h2d_bytes"] += f_k.nbytes
             f_k = _to_dev(ops, f_k)
         blk = g1 - g0
-        if fx_k is None or fx_k.shape[1] != blk:
-            fx_k = torch.empty((nkpt, blk, nip), dtype=torch.complex128, device=dev)
-        ops.gram_conja(f_k, xip, out=fx_k)                                    # :76
-        ops.ktransform_square(fx_k, blk * nip, nip, theta, nipP * ncol, 1, ncol, g0 - g_lo, blk, nip, kmesh, uax,
-                              conj2=0, out_g_fast=1, qslot=qslot, rowmap=rowmap, rowmap_sq=nip,
-                              diag=diag[2:4])                                 # :79-85
+        if fx_k is None or fx_k.numel() != nkpt * blk * nip:
+            fx_k = torch.empty((nkpt * blk * nip,), dtype=torch.complex128, device=dev)
+        if reg_path:
+            # transposed product fx^T[k][I][g] = X_k F_k^H (:76), so the elementwise stage streams along g
+            fxt = fx_k.view(nkpt, nip, blk)
+            ops.gram_conjb(xip, f_k, out=fxt)
+            ops.ktransform_rows(fxt, nip * blk, blk, theta, nipP * ncol, ncol, g0 - g_lo, nip, blk, kmesh, uax_h,
+                                conj2=0, qslot=qslot, rowmap=rowmap, rowmap_sq=nip, diag=diag[2:4])   # :79-85
+        else:
+            fx = fx_k.view(nkpt, blk, nip)
+            ops.gram_conja(f_k, xip, out=fx)                                  # :76
+            ops.ktransform_square(fx, blk * nip, nip, theta, nipP * ncol, 1, ncol, g0 - g_lo, blk, nip, kmesh, uax,
+                                  conj2=0, out_g_fast=1, qslot=qslot, rowmap=rowmap, rowmap_sq=nip,
+                                  diag=diag[2:4])                             # :79-85
         _log(df_obj, "finished aoR_loop[%8d:%8d]", g0, g1)
     del fx_k
     df_obj._ao_tables_dev = None

@@ -85,6 +85,20 @@ class IsdfOps:
         self.launches += 1
         return out
 
+    def gram_conjb(self, a, b, out=None):
+        """out[z] = a[z] @ conj(b[z])^T  (a [m,k], b [n,k] strided views with unit-stride last axis)."""
+        assert a.is_cuda and b.is_cuda and a.dtype == c128 and b.dtype == c128
+        assert a.stride(2) == 1 and b.stride(2) == 1
+        batch, m, k = a.shape
+        _, n, _ = b.shape
+        if out is None:
+            out = torch.empty((batch, m, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gram_conjb(self.h, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1),
+                                                   b.stride(0), _ptr(out), n, m * n, m, n, k, batch, _stream()),
+                          "isdf_gram_conjb")
+        self.launches += 1
+        return out
+
     def gemm_nn(self, a, b):
         _chk(a, c128), _chk(b, c128)
         batch, m, k = a.shape
@@ -96,6 +110,29 @@ class IsdfOps:
         return out
 
     # ---- k<->R transform, square, k<->R transform ------------------------------------------
+    def ktransform_rows(self, vin, in_sk, in_sr, out, out_sq, out_sr, out_c0, nrows, ncols, kmesh, uaxes_host, conj2,
+                        qslot=None, rowmap=None, rowmap_sq=0, diag=None):
+        """Register-resident k-transform (small k-meshes).  Returns False when the mesh is unsupported."""
+        km = (C.c_int * 3)(*[int(x) for x in kmesh])
+        assert uaxes_host.dtype == np.complex128 and uaxes_host.shape == (3, KT_NMAX, KT_NMAX)
+        rc = self.lib.isdf_ktransform_square_rows(
+            self.h, _ptr(vin), in_sk, in_sr, _ptr(out), out_sq, out_sr, out_c0, nrows, ncols, km,
+            C.c_void_p(uaxes_host.ctypes.data), int(conj2), _ptr(qslot), _ptr(rowmap), rowmap_sq, _ptr(diag),
+            _stream())
+        if rc == -2:
+            return False
+        self.handle.check(rc, "isdf_ktransform_square_rows")
+        self.launches += 1
+        return True
+
+    def pack_uaxes_host(self, kmesh):
+        from .pbc_tools import get_phase_axes
+        u = np.zeros((3, KT_NMAX, KT_NMAX), dtype=np.complex128)
+        for a, m in enumerate(get_phase_axes(kmesh)):
+            assert m.shape[0] <= KT_NMAX, "k-mesh axis > 8 not supported by the k-transform kernels"
+            u[a, : m.shape[0], : m.shape[1]] = m
+        return u
+
     def pack_uaxes(self, kmesh):
         from .pbc_tools import get_phase_axes
         u = np.zeros((3, KT_NMAX, KT_NMAX), dtype=np.complex128)

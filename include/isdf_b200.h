@@ -50,6 +50,10 @@ int isdf_pchol(void* handle, void* a, int n, int batch, int max_steps, double to
 int isdf_gram_conja(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
                     void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream);
 
+/* transposed form of :76:  c[z][i][j] = sum_l a[z][i][l] * conj(b[z][j][l])  (fx_k^T = X_k F_k^H). */
+int isdf_gram_conjb(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                    void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream);
+
 /* plain batched complex GEMM c[z] = a[z] b[z], a [m][k], b [k][n] (the kernel behind the sweeps). */
 int isdf_gemm_nn(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
                  void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream);
@@ -65,6 +69,15 @@ int isdf_ktransform_square(void* handle, const void* in, long in_sk, long in_sg,
                            long out_si, long out_g0, int ng, int ni, const int* kmesh, const void* uaxes, int conj2,
                            int out_g_fast, const int* qslot, const int* rowmap, long rowmap_sq, double* diag,
                            void* stream);
+
+/* Register-resident variant of isdf_ktransform_square for small k-meshes (every axis <= 4, nk <= 32):
+ * in[k*in_sk + r*in_sr + c] (c contiguous) -> out[slot*out_sq + row*out_sr + out_c0 + c], row = rowmap[slot][r].
+ * uaxes is a HOST pointer here (3 x [8][8] c128, copied to constant memory).  Returns -2 without launching
+ * when the mesh has no instantiation (use isdf_ktransform_square then). */
+int isdf_ktransform_square_rows(void* handle, const void* in, long in_sk, long in_sr, void* out, long out_sq,
+                                long out_sr, long out_c0, int nrows, int ncols, const int* kmesh,
+                                const void* uaxes_host, int conj2, const int* qslot, const int* rowmap,
+                                long rowmap_sq, double* diag, void* stream);
 
 /* fftisdf.py:108  scipy.linalg.lstsq(A_q, Y_q^T): block operators of the two triangular sweeps from the
  * pivoted factor (block size 64).  n = nip, nP = multiple of 64 >= max(rank) (usually n rounded up).  lfwd, ubwd [batch][nP][nP];

@@ -254,3 +254,52 @@ def test_device_coulomb_weights_and_phase(ops, mesh, kmesh):
         assert relerr(got, ref) < 1e-13
         ops.phase_table(cd, kpts[q], f)
         assert relerr(f.cpu().numpy(), np.exp(-1j * coords @ kpts[q])) < 1e-13
+
+
+@pytest.mark.parametrize("kmesh", [[1, 1, 1], [2, 2, 2], [3, 3, 3], [3, 2, 1], [1, 4, 4], [2, 4, 4], [4, 4, 4], [5, 1, 1]])
+def test_ktransform_rows_register_path(ops, kmesh):
+    """Register-resident k-transform == dense phase-matrix arithmetic of the reference (or a clean
+    'unsupported' for meshes that must use the shared-memory kernel)."""
+    rng = np.random.default_rng(13)
+    nk = int(np.prod(kmesh))
+    a = np.eye(3) * 6.0 + 0.3 * rng.standard_normal((3, 3))
+    phase = H.get_phase(a, H.get_kpts(a, kmesh), kmesh)
+    nrows, ncols = 11, 203
+    vs = rng.standard_normal((nk, nrows * ncols))
+    vk = (phase.conj().T @ vs).reshape(nk, nrows, ncols)
+    qslot = np.arange(nk, dtype=np.int32)
+    qslot[nk // 2] = -1 if nk > 1 else 0
+    rowmap = np.stack([rng.permutation(nrows) for _ in range(nk)]).astype(np.int32)
+    rowmap[0, 2] = -1
+    out = torch.zeros((nk, nrows, 300), dtype=torch.complex128, device="cuda")
+    diag = torch.zeros(2, dtype=torch.float64, device="cuda")
+    ok = ops.ktransform_rows(dev(vk), nrows * ncols, ncols, out, nrows * 300, 300, 7, nrows, ncols, kmesh,
+                             ops.pack_uaxes_host(kmesh), conj2=0, qslot=dev(qslot), rowmap=dev(rowmap), rowmap_sq=nrows,
+                             diag=diag)
+    if nk > 32 or max(kmesh) > 4:
+        assert not ok
+        return
+    assert ok
+    ys = phase @ vk.reshape(nk, -1)
+    full = (phase.T @ (ys * ys)).reshape(nk, nrows, ncols)
+    got = out.cpu().numpy()
+    for q in range(nk):
+        ref = np.zeros((nrows, 300), complex)
+        if qslot[q] >= 0:
+            for r in range(nrows):
+                if rowmap[qslot[q], r] >= 0:
+                    ref[rowmap[qslot[q], r], 7:7 + ncols] = full[q, r]
+            assert relerr(got[qslot[q]], ref) < 1e-13
+    assert diag.cpu().numpy()[0] < 1e-12
+    out2 = torch.zeros((nk, nrows, ncols), dtype=torch.complex128, device="cuda")
+    assert ops.ktransform_rows(dev(vk), nrows * ncols, ncols, out2, nrows * ncols, ncols, 0, nrows, ncols, kmesh,
+                               ops.pack_uaxes_host(kmesh), conj2=1)
+    ref2 = (phase.conj().T @ (ys * ys)).reshape(nk, nrows, ncols)
+    assert relerr(out2.cpu().numpy(), ref2) < 1e-13
+
+
+def test_gram_conjb(ops):
+    rng = np.random.default_rng(14)
+    a, b = crand(rng, 3, 150, 26), crand(rng, 3, 333, 26)
+    c = ops.gram_conjb(dev(a), dev(b)).cpu().numpy()
+    assert relerr(c, np.einsum("zik,zjk->zij", a, b.conj())) < 1e-13

@@ -1,13 +1,15 @@
 // FP64 complex GEMM tile engine for sm_100a.
 //
 // Complex128 operands stay in numpy/torch interleaved (re,im) layout end to end.  Tiles are
-// staged global -> shared with a 3-deep cp.async (LDGSTS) ring; each lane pulls one complex
+// staged global -> shared with a cp.async (LDGSTS) ring; each lane pulls one complex
 // element per fragment with a single conflict-free LDS.128 and feeds the re/im halves to the
 // FP64 tensor pipe (mma.sync.m8n8k4.f64 == DMMA.8x8x4, the only FP64 MMA sm_100a has; tcgen05
 // has no f64 kind).  One complex MAC = 4 DMMA lanes-worth of FMAs (the "4M" form).
 //
-// CTA = 512 threads = 16 warps, warp tile 32(m) x 16(n) complex, CTA tile BM x BN with
-// (BM/32)*(BN/16) == 16, i.e. 128x64 or 64x128.  K step 16 complex per stage, 3 stages (measured: +5 % over 8x4).
+// Default configuration (measured best on B200, profiles/r1_gemm_variants.txt): CTA tile 64x64 complex,
+// 256 threads = 8 warps of 32(m) x 16(n), K step 16 complex, 2-stage cp.async ring, TWO CTAs per SM so
+// that one CTA's barrier / prologue / epilogue bubbles are filled by the other (92 % of cuBLAS DGEMM).
+// ISDF_GEMM_SMALL=0 selects the 512-thread 128x64 / 64x128 tiles (one CTA per SM, 86 %).
 //
 // Operand layouts: KCONTIG = [rows][K] row-major (K fastest), KSLOW = [K][rows] (rows fastest).
 #pragma once
@@ -33,11 +35,15 @@ struct GemmParams {
 #define ISDF_GEMM_BK 16
 #endif
 #ifndef ISDF_GEMM_STAGES
-#define ISDF_GEMM_STAGES 3
+#define ISDF_GEMM_STAGES 2
+#endif
+#ifndef ISDF_GEMM_SMALL
+#define ISDF_GEMM_SMALL 1     // 1: 64x64 tiles, 256 threads, 2 CTAs per SM; 0: 128x64 / 64x128 tiles, 512 threads
 #endif
 constexpr int GEMM_BK = ISDF_GEMM_BK;        // complex K elements per pipeline stage (multiple of 4)
 constexpr int GEMM_STAGES = ISDF_GEMM_STAGES;
-constexpr int GEMM_THREADS = 512;
+__host__ __device__ constexpr int gemm_threads(int BM, int BN) { return (BM / 32) * (BN / 16) * 32; }
+__host__ __device__ constexpr int gemm_min_blocks(int BM, int BN) { return gemm_threads(BM, BN) <= 256 ? 2 : 1; }
 
 template <int BM, int BN, bool A_KSLOW, bool B_KSLOW>
 struct GemmSmem {
@@ -49,8 +55,9 @@ struct GemmSmem {
 };
 
 template <int BM, int BN, bool A_KSLOW, bool B_KSLOW, int MODE, bool REAL_ONLY, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(GemmParams p) {
-  static_assert((BM / 32) * (BN / 16) == 16, "16 warps of 32x16");
+__global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN)) gemm_c128_kernel(GemmParams p) {
+  static_assert(BM % 32 == 0 && BN % 16 == 0, "warp tile is 32x16");
+  constexpr int GEMM_THREADS = gemm_threads(BM, BN);
   constexpr int BK = GEMM_BK, STAGES = GEMM_STAGES;
   using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW>;
   constexpr int LDA_S = S::LDA_S, LDB_S = S::LDB_S, A_TILE = S::A_TILE, B_TILE = S::B_TILE;
@@ -227,8 +234,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_c128_kernel(GemmParams p
   }
 }
 
-template <int BM, int BN, bool A_KSLOW, bool B_KSLOW, int MODE, bool REAL_ONLY, int EPI>
+template <int BM_, int BN_, bool A_KSLOW, bool B_KSLOW, int MODE, bool REAL_ONLY, int EPI>
 inline cudaError_t launch_gemm(const GemmParams& p, int batch, cudaStream_t st) {
+  constexpr int BM = ISDF_GEMM_SMALL ? 64 : BM_;
+  constexpr int BN = ISDF_GEMM_SMALL ? 64 : BN_;
   using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW>;
   auto kern = gemm_c128_kernel<BM, BN, A_KSLOW, B_KSLOW, MODE, REAL_ONLY, EPI>;
   static bool configured = false;
@@ -239,7 +248,7 @@ inline cudaError_t launch_gemm(const GemmParams& p, int batch, cudaStream_t st) 
   }
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
-  kern<<<grid, GEMM_THREADS, S::BYTES, st>>>(p);
+  kern<<<grid, gemm_threads(BM, BN), S::BYTES, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -16,7 +16,10 @@
 // matrices of the batch concurrently) produces nb rows of U; the trailing update
 // A -= U_panel^H U_panel runs on the DMMA GEMM engine.
 #include <float.h>
+#include <cooperative_groups.h>
 #include "gemm_c128.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace isdf {
 
@@ -188,6 +191,195 @@ pchol_panel_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n,
     if (i < n) pos[i] = mypos[c];
   }
   if (!stopped && tid == 0) { info->rank = j0 + steps_done; info->dstop = dstop; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cluster version of the panel kernel for large matrices: one thread-block cluster of PCC_CS CTAs per
+// matrix, each CTA owning a contiguous slice of columns whose in-panel rows of U stay in ITS shared
+// memory.  Per step there are two cluster barriers: (1) every CTA publishes its best candidate into
+// every CTA's shared memory (DSMEM stores) and all reduce the PCC_CS candidates identically; (2) the
+// CTA that owns the pivot column broadcasts that column's in-panel entries.  Same arithmetic and pivot
+// rule as pchol_panel_kernel.
+constexpr int PCC_CS = 8;        // portable cluster size
+constexpr int PCC_THREADS = 512;
+constexpr int PCC_NCOL = 2;      // columns per thread -> ncc <= 1024, n <= 8192
+
+struct PcCand { double v; int pos; int idx; };
+
+__global__ void __cluster_dims__(PCC_CS, 1, 1) __launch_bounds__(PCC_THREADS, 1)
+pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n, int ncc, int j0, int nb,
+                           int max_steps, double tol, cplx* Uall, long ldu, long strideU, int* posall,
+                           PcholInfo* infoall, int* active) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  PcholInfo* info = infoall + b;
+  if (info->done) return;   // uniform over the cluster (flag is only written after a cluster barrier)
+  const cplx* A = Aall + (long)b * strideA;
+  cplx* U = Uall + (long)b * strideU;
+  int* pos = posall + (long)b * n;
+
+  extern __shared__ __align__(16) unsigned char pcc_smem[];
+  cplx* up = reinterpret_cast<cplx*>(pcc_smem);                 // [nb][ncc] in-panel rows of U, own columns
+  double* s_aii = reinterpret_cast<double*>(up + (long)nb * ncc);  // [ncc]
+  __shared__ cplx bp[PC_NB_MAX];
+  __shared__ PcCand cand[PCC_CS];
+  __shared__ double red_v[PCC_THREADS / 32];
+  __shared__ int red_pos[PCC_THREADS / 32];
+  __shared__ int red_idx[PCC_THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c_lo = crank * ncc;
+  double ssum[PCC_NCOL];
+  int mypos[PCC_NCOL];
+#pragma unroll
+  for (int c = 0; c < PCC_NCOL; ++c) {
+    const int lc = tid + c * PCC_THREADS;
+    const int i = c_lo + lc;
+    ssum[c] = 0.0;
+    if (lc < ncc && i < n) {
+      s_aii[lc] = A[(long)i * lda + i].x;
+      mypos[c] = pos[i];
+    } else {
+      mypos[c] = -1;
+    }
+  }
+  double dstop = info->dstop;
+  int steps_done = 0;
+  bool stopped = false;
+
+  for (int t = 0; t <= nb; ++t) {
+    const int j = j0 + t;
+    if (t == nb && j < max_steps) break;
+    // ---- 1. local candidate
+    double bv = -DBL_MAX;
+    int bpos = 0x7fffffff, bidx = -1;
+#pragma unroll
+    for (int c = 0; c < PCC_NCOL; ++c) {
+      if (mypos[c] >= j) {
+        const int lc = tid + c * PCC_THREADS;
+        const double d = s_aii[lc] - ssum[c];
+        if (d > bv || (d == bv && mypos[c] < bpos)) { bv = d; bpos = mypos[c]; bidx = c_lo + lc; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > bv || (ov == bv && op < bpos)) { bv = ov; bpos = op; bidx = oi; }
+    }
+    if (lane == 0) { red_v[warp] = bv; red_pos[warp] = bpos; red_idx[warp] = bidx; }
+    __syncthreads();
+    if (warp == 0) {
+      if (lane < PCC_THREADS / 32) { bv = red_v[lane]; bpos = red_pos[lane]; bidx = red_idx[lane]; }
+      else { bv = -DBL_MAX; bpos = 0x7fffffff; bidx = -1; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ov > bv || (ov == bv && op < bpos)) { bv = ov; bpos = op; bidx = oi; }
+      }
+      if (lane < PCC_CS) {   // lane r publishes this CTA's candidate into CTA r's table
+        PcCand* remote = cluster.map_shared_rank(cand, lane);
+        remote[crank].v = bv; remote[crank].pos = bpos; remote[crank].idx = bidx;
+      }
+    }
+    cluster.sync();
+    // ---- 2. identical reduction of the PCC_CS candidates in every CTA
+    double dp = -DBL_MAX;
+    int ppos = 0x7fffffff, p = -1;
+#pragma unroll
+    for (int r = 0; r < PCC_CS; ++r) {
+      const double ov = cand[r].v;
+      const int op = cand[r].pos, oi = cand[r].idx;
+      if (ov > dp || (ov == dp && op < ppos)) { dp = ov; ppos = op; p = oi; }
+    }
+    if (j == 0) dstop = (tol < 0.0) ? (double)n * DBL_EPSILON * dp : tol;
+    if (p < 0 || j >= max_steps || !(dp > dstop) || !(dp > 0.0)) {
+      if (crank == 0 && tid == 0) {
+        info->rank = j; info->done = 1; info->dstop = dstop;
+        info->next = (p < 0) ? 0.0 : dp;
+        active[b] = 0;
+      }
+      stopped = true;
+      break;
+    }
+    // ---- 3. positions
+#pragma unroll
+    for (int c = 0; c < PCC_NCOL; ++c) {
+      const int i = c_lo + tid + c * PCC_THREADS;
+      if (mypos[c] >= 0) {
+        if (i == p) mypos[c] = j;
+        else if (mypos[c] == j) mypos[c] = ppos;
+      }
+    }
+    // ---- 4. owner CTA broadcasts the pivot column's in-panel entries to every CTA
+    const int owner = p / ncc;
+    if (crank == owner) {
+      const int pl = p - c_lo;
+      for (int w = tid; w < t * PCC_CS; w += PCC_THREADS) {
+        const int tt = w / PCC_CS, r = w - tt * PCC_CS;
+        cplx* remote = cluster.map_shared_rank(bp, r);
+        remote[tt] = up[(long)tt * ncc + pl];
+      }
+    }
+    cluster.sync();
+    // ---- 5. new row of U for the own columns
+    const double rt = sqrt(dp);
+    const double inv = 1.0 / rt;
+    const cplx* Arow = A + (long)p * lda;
+    cplx v[PCC_NCOL];
+    bool act[PCC_NCOL];
+#pragma unroll
+    for (int c = 0; c < PCC_NCOL; ++c) {
+      const int lc = tid + c * PCC_THREADS;
+      const int i = c_lo + lc;
+      act[c] = (lc < ncc) && (i < n) && (i != p) && (mypos[c] > j);
+      v[c] = act[c] ? Arow[i] : make_double2(0.0, 0.0);
+    }
+    for (int tt = 0; tt < t; ++tt) {
+      const cplx bb = bp[tt];
+#pragma unroll
+      for (int c = 0; c < PCC_NCOL; ++c) {
+        if (act[c]) {
+          const cplx ui = up[(long)tt * ncc + tid + c * PCC_THREADS];
+          v[c].x -= bb.x * ui.x + bb.y * ui.y;   // v -= conj(bb) * ui
+          v[c].y -= bb.x * ui.y - bb.y * ui.x;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < PCC_NCOL; ++c) {
+      const int lc = tid + c * PCC_THREADS;
+      const int i = c_lo + lc;
+      if (lc < ncc && i < n) {
+        cplx u;
+        if (i == p) {
+          u = make_double2(rt, 0.0);
+        } else if (act[c]) {
+          u = make_double2(v[c].x * inv, v[c].y * inv);
+          ssum[c] += u.x * u.x + u.y * u.y;
+        } else {
+          u = make_double2(0.0, 0.0);
+        }
+        if (t < nb) up[(long)t * ncc + lc] = u;
+        U[(long)j * ldu + i] = u;
+      }
+    }
+    steps_done = t + 1;
+    __syncthreads();   // up[t][*] visible to the owner's broadcast of the next step
+  }
+#pragma unroll
+  for (int c = 0; c < PCC_NCOL; ++c) {
+    const int lc = tid + c * PCC_THREADS;
+    const int i = c_lo + lc;
+    if (lc < ncc && i < n) pos[i] = mypos[c];
+  }
+  if (!stopped && crank == 0 && tid == 0) { info->rank = j0 + steps_done; info->dstop = dstop; }
+  // keep every CTA's shared memory alive until all remote stores into it have been consumed
+  cluster.sync();
 }
 
 __global__ void pchol_finalize_kernel(const int* pos, const PcholInfo* info, int n, int batch, int* piv, int* rank,
@@ -367,10 +559,27 @@ extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, do
   const long strideA = (long)n * n, strideU = (long)ldu_rows * n;
   ISDF_CUDA(h, cudaFuncSetAttribute(pchol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     PC_THREADS * PC_NCOL * (int)sizeof(double)));
+  // Large matrices: one 8-CTA cluster per matrix with the panel held in distributed shared memory.
+  const bool use_cluster = (n >= 256);
+  const int ncc = (n + PCC_CS - 1) / PCC_CS;
+  size_t csmem = 0;
+  if (use_cluster) {
+    const long avail = 200 * 1024 - (long)ncc * (long)sizeof(double);
+    const int nb_fit = (int)(avail / ((long)ncc * (long)sizeof(cplx)));
+    ISDF_CHECK_ARG(h, nb_fit >= 4 && ncc <= PCC_THREADS * PCC_NCOL, "matrix too large for the cluster panel kernel");
+    if (nb > nb_fit) nb = nb_fit;
+    csmem = (size_t)nb * ncc * sizeof(cplx) + (size_t)ncc * sizeof(double);
+    ISDF_CUDA(h, cudaFuncSetAttribute(pchol_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+  }
   // The panel that reaches max_steps also evaluates the would-be next pivot and sets the stop flag.
   for (int j0 = 0; j0 == 0 || j0 < max_steps; j0 += nb) {
-    pchol_panel_kernel<<<batch, PC_THREADS, (size_t)n * sizeof(double), st>>>((const cplx*)a, n, strideA, n, j0, nb, max_steps, tol, (cplx*)u, n,
-                                                     strideU, pos, info, active);
+    if (use_cluster) {
+      pchol_panel_cluster_kernel<<<dim3(PCC_CS, batch), PCC_THREADS, csmem, st>>>(
+          (const cplx*)a, n, strideA, n, ncc, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);
+    } else {
+      pchol_panel_kernel<<<batch, PC_THREADS, (size_t)n * sizeof(double), st>>>(
+          (const cplx*)a, n, strideA, n, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);
+    }
     ISDF_LAUNCH_CHECK(h);
     if (j0 + nb < max_steps) {
       // trailing update A -= U_p^H U_p (only needed while further pivot rows will be read)

@@ -72,7 +72,8 @@ def _psd(rng, n, r, complex_=True):
     return b @ b.conj().T
 
 
-@pytest.mark.parametrize("n,r,nb", [(200, 200, 32), (130, 40, 16), (300, 300, 64), (65, 65, 7)])
+@pytest.mark.parametrize("n,r,nb", [(200, 200, 32), (130, 40, 16), (300, 300, 64), (65, 65, 7), (1100, 300, 32),
+                                    (2051, 2051, 32)])
 def test_pchol_complex(ops, n, r, nb):
     rng = np.random.default_rng(5)
     a = np.stack([_psd(rng, n, r), _psd(rng, n, r)])
@@ -303,3 +304,16 @@ def test_gram_conjb(ops):
     a, b = crand(rng, 3, 150, 26), crand(rng, 3, 333, 26)
     c = ops.gram_conjb(dev(a), dev(b)).cpu().numpy()
     assert relerr(c, np.einsum("zik,zjk->zij", a, b.conj())) < 1e-13
+
+
+def test_pchol_cluster_matches_dpstrf_large(ops):
+    """n >= 256 runs on the 8-CTA cluster panel kernel (DSMEM): same pivots as LAPACK dpstrf."""
+    rng = np.random.default_rng(15)
+    n = 1500
+    x = rng.standard_normal((n, 40))
+    x4 = (x @ x.T) ** 2
+    _, piv_ref, _ = H.pivoted_cholesky(x4.copy())
+    nsteps = 333
+    u, piv, rank, nxt = ops.pchol(dev(x4[None].astype(complex)), max_steps=nsteps, tol=-1.0, nb=32)
+    assert int(rank.cpu()[0]) == nsteps
+    assert np.array_equal(piv.cpu().numpy()[0][:nsteps], piv_ref[:nsteps])

@@ -155,6 +155,39 @@ class SyntheticCell:
     def eval_ao_kpts(self, coords, kpts):
         return np.asarray(self.pbc_eval_gto("GTOval", coords, kpts=kpts))
 
+    # ---- device evaluation (same functions, libisdf_b200's ao_eval kernel) ---------------------
+    def _ao_desc_bytes(self):
+        """Pack the AO list in the record layout of csrc/ao_eval.cu::AoDesc."""
+        dt = np.dtype([("c", "<f8", 3), ("alpha", "<f8"), ("norm", "<f8"), ("coef", "<f8", 3), ("pw", "<i4", (3, 3)),
+                       ("nterm", "<i4")], align=True)
+        rec = np.zeros(self.nao_nr(), dtype=dt)
+        for mu, terms in enumerate(self._terms):
+            rec["c"][mu] = self._cen[mu]
+            rec["alpha"][mu] = self._alp[mu]
+            rec["norm"][mu] = self._norm[mu]
+            rec["nterm"][mu] = len(terms)
+            for i, (coef, pw) in enumerate(terms):
+                rec["coef"][mu][i] = coef
+                rec["pw"][mu][i] = pw
+        return rec
+
+    def eval_ao_device(self, ops, coords, kpts, out=None):
+        """[nk, npts, nao] complex128 CUDA tensor; `coords` numpy [npts,3] or CUDA tensor."""
+        import torch
+        key = id(ops)
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        if key not in cache:
+            rec = self._ao_desc_bytes()
+            assert rec.dtype.itemsize == ops.lib.isdf_ao_desc_bytes(), (rec.dtype.itemsize, ops.lib.isdf_ao_desc_bytes())
+            cache[key] = (torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(ops.device),
+                          torch.from_numpy(np.ascontiguousarray(self._images)).to(ops.device))
+        desc, images = cache[key]
+        kpts = np.asarray(kpts, dtype=np.float64).reshape(-1, 3)
+        kphase = torch.from_numpy(np.ascontiguousarray(np.exp(1j * (kpts @ self._images.T)))).to(ops.device)
+        if not torch.is_tensor(coords):
+            coords = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(ops.device)
+        return ops.eval_ao(coords.contiguous(), desc, self.nao_nr(), images, kphase, out=out)
+
 
 def random_cubic_cell(ng_side, nao, seed, L=None, alpha_range=(0.3, 3.0), ltypes="s"):
     """SURVEY.md section 8(d) synthetic family: cubic cell, side L = 10 bohr * (ng/32^3)^(1/3), `nao`

@@ -1,5 +1,5 @@
 // Register-resident variant of the k<->R transform / square / k<->R transform for small k-meshes
-// (nk <= 32, every axis <= 4): one thread owns all nk values of one element, so there is no shared
+// (every axis <= 4): one thread (nk <= 32) or four lanes (nk <= 64) own all nk values of one element, so there is no shared
 // memory, no barrier and the input/output accesses are plain coalesced streams.  Same arithmetic and
 // reference lines as ktransform.cu (fftisdf.py:41-47, :79-85).  Input is [nk][rows][cols] with cols
 // contiguous; for the right-hand side the GEMM already produces the transposed fx^T[k][i][g], so the
@@ -99,6 +99,98 @@ __global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
   }
 }
 
+// Lane-split variant for 32 < nk <= 64 with one axis of length 4: four lanes share an element, each holding
+// the slab with split-axis index `sub`; the two local axes are transformed in registers, the split axis with
+// warp shuffles.  Lane = sub*8 + e, so the 8 elements of a warp stay contiguous in memory per slab.
+template <int N1, int N2, int N3, int SA, bool CONJ>
+__device__ __forceinline__ void kt_split_transform(cplx (&x)[(N1 * N2 * N3) / 4], int sub, int lane) {
+  constexpr int NA = (SA == 0) ? N2 : N1;
+  constexpr int NB = (SA == 2) ? N2 : N3;
+  constexpr int AXA = (SA == 0) ? 1 : 0;
+  constexpr int AXB = (SA == 2) ? 1 : 2;
+  constexpr int NL = NA * NB;
+  dft_axis<NB, 1, NL, AXB, CONJ>(x);
+  dft_axis<NA, NB, NL, AXA, CONJ>(x);
+  const int e = lane & 7;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cplx v;
+      v.x = __shfl_sync(0xffffffffu, x[l].x, j * 8 + e);
+      v.y = __shfl_sync(0xffffffffu, x[l].y, j * 8 + e);
+      cplx u = c_uax[SA][sub][j];
+      if (CONJ) u.y = -u.y;
+      cfma(acc, u, v);
+    }
+    x[l] = acc;
+  }
+}
+
+template <int N1, int N2, int N3, int SA>
+__global__ void __launch_bounds__(128) ktransform_split_kernel(KtRegParams p) {
+  static_assert(((SA == 0) ? N1 : (SA == 1) ? N2 : N3) == 4, "split axis must have length 4");
+  constexpr int NA = (SA == 0) ? N2 : N1;
+  constexpr int NB = (SA == 2) ? N2 : N3;
+  constexpr int NL = NA * NB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, e = lane & 7;
+  const int c = (blockIdx.x * 4 + warp) * 8 + e;
+  const int r = blockIdx.y;
+  const bool valid = c < p.ncols;
+  auto kof = [&](int l) {
+    const int a = l / NB, b = l % NB;
+    return (SA == 0) ? ((sub * N2 + a) * N3 + b) : (SA == 1) ? ((a * N2 + sub) * N3 + b) : ((a * N2 + b) * N3 + sub);
+  };
+  cplx x[NL];
+  const cplx* src = p.in + (long)r * p.in_sr + (valid ? c : 0);
+#pragma unroll
+  for (int l = 0; l < NL; ++l) x[l] = valid ? src[(long)kof(l) * p.in_sk] : make_double2(0.0, 0.0);
+  kt_split_transform<N1, N2, N3, SA, false>(x, sub, lane);
+  double mx_im = 0.0, mx_re = 0.0;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    mx_im = fmax(mx_im, fabs(x[l].y));
+    mx_re = fmax(mx_re, fabs(x[l].x));
+    x[l] = make_double2(x[l].x * x[l].x, 0.0);
+  }
+  if (p.conj2) kt_split_transform<N1, N2, N3, SA, true>(x, sub, lane);
+  else kt_split_transform<N1, N2, N3, SA, false>(x, sub, lane);
+  if (valid) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int q = kof(l);
+      const int slot = p.qslot ? p.qslot[q] : q;
+      if (slot < 0) continue;
+      int row = r;
+      if (p.rowmap) {
+        row = p.rowmap[(long)slot * p.rowmap_sq + r];
+        if (row < 0) continue;
+      }
+      p.out[(long)slot * p.out_sq + (long)row * p.out_sr + p.out_c0 + c] = x[l];
+    }
+  }
+  if (p.diag != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx_im = fmax(mx_im, __shfl_xor_sync(0xffffffffu, mx_im, o));
+      mx_re = fmax(mx_re, __shfl_xor_sync(0xffffffffu, mx_re, o));
+    }
+    if (lane == 0) {
+      atomic_max_nonneg(p.diag + 0, mx_im);
+      atomic_max_nonneg(p.diag + 1, mx_re);
+    }
+  }
+}
+
+template <int N1, int N2, int N3, int SA>
+static cudaError_t launch_split(const KtRegParams& p, cudaStream_t st) {
+  dim3 grid((p.ncols + 31) / 32, p.nrows);
+  ktransform_split_kernel<N1, N2, N3, SA><<<grid, 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int N1, int N2, int N3>
 static cudaError_t launch_reg(const KtRegParams& p, cudaStream_t st) {
   dim3 grid((p.ncols + 127) / 128, p.nrows);
@@ -124,7 +216,7 @@ extern "C" int isdf_ktransform_square_rows(void* hv, const void* in, long in_sk,
   ISDF_CHECK_ARG(h, in && out && kmesh && uaxes_host, "null pointer");
   const int n1 = kmesh[0], n2 = kmesh[1], n3 = kmesh[2];
   ISDF_CHECK_ARG(h, n1 >= 1 && n2 >= 1 && n3 >= 1, "kmesh");
-  if (n1 > 4 || n2 > 4 || n3 > 4 || n1 * n2 * n3 > 32) return ISDF_ESIZE;
+  if (n1 > 4 || n2 > 4 || n3 > 4) return ISDF_ESIZE;
   ISDF_CHECK_ARG(h, nrows <= 65535, "too many rows for one launch");
   if (nrows <= 0 || ncols <= 0) return ISDF_OK;
   ISDF_CUDA(h, cudaMemcpyToSymbolAsync(c_uax, uaxes_host, sizeof(cplx) * 3 * 64, 0, cudaMemcpyHostToDevice, st));
@@ -142,6 +234,10 @@ extern "C" int isdf_ktransform_square_rows(void* hv, const void* in, long in_sk,
   KT_CASE(2, 3, 1) KT_CASE(3, 1, 2) KT_CASE(3, 2, 1) KT_CASE(1, 1, 4) KT_CASE(1, 4, 1) KT_CASE(4, 1, 1)
   KT_CASE(2, 2, 4) KT_CASE(2, 4, 2) KT_CASE(4, 2, 2) KT_CASE(1, 4, 4) KT_CASE(4, 1, 4) KT_CASE(4, 4, 1)
   KT_CASE(2, 4, 4) KT_CASE(4, 2, 4) KT_CASE(4, 4, 2)
+#define KT_SPLIT(a, b, c, sa) \
+  if (n1 == a && n2 == b && n3 == c) { e = launch_split<a, b, c, sa>(p, st); hit = true; }
+  KT_SPLIT(4, 4, 4, 0) KT_SPLIT(3, 4, 4, 1) KT_SPLIT(4, 3, 4, 0) KT_SPLIT(4, 4, 3, 0) KT_SPLIT(4, 3, 3, 0)
+  KT_SPLIT(3, 4, 3, 1) KT_SPLIT(3, 3, 4, 2)
   if (!hit) return ISDF_ESIZE;
   ISDF_CUDA(h, e);
   return ISDF_OK;

@@ -461,6 +461,8 @@ class InterpolativeSeparableDensityFitting(_Base):
                 ao = t[:, p0 - off:p1 - off, :]
             elif host_tab is not None:
                 ao = host_tab[:, p0:p1, :]
+            elif getattr(self, "ao_on_device", True) and hasattr(cell, "eval_ao_device"):
+                ao = cell.eval_ao_device(self._ops, c, kpts)
             else:
                 ao = numpy.asarray(cell.pbc_eval_gto("GTOval", c, kpts=kpts))
             yield (ao, ao, None, None, c), p0, p1
@@ -481,6 +483,8 @@ class InterpolativeSeparableDensityFitting(_Base):
         nao = pcell.nao_nr()
         if x0 is None:
             x0 = getattr(self, "_x0_table", None)
+        if x0 is None and getattr(self, "ao_on_device", True) and hasattr(pcell, "eval_ao_device"):
+            x0 = pcell.eval_ao_device(ops, pcell.gen_uniform_grids(m0), self.kpts)          # :367-370 on the device
         if x0 is None:
             x0 = pcell.pbc_eval_gto("GTOval", pcell.gen_uniform_grids(m0), kpts=self.kpts)   # :367-370
             x0 = numpy.asarray(x0)                                                         # :371

@@ -217,6 +217,18 @@ class IsdfOps:
                                                     _stream()), "isdf_phase_table")
         self.launches += 1
 
+    # ---- periodic Gaussian AO evaluation (input producer for SyntheticCell) ---------------------
+    def eval_ao(self, coords_dev, ao_desc_dev, nao, images_dev, kphase_dev, out=None):
+        npts = coords_dev.shape[0]
+        nk, nimg = kphase_dev.shape
+        if out is None:
+            out = torch.empty((nk, npts, nao), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_eval_ao(self.h, _ptr(coords_dev), npts, _ptr(ao_desc_dev), nao,
+                                                _ptr(images_dev), nimg, _ptr(kphase_dev), nk, _ptr(out), _stream()),
+                          "isdf_eval_ao")
+        self.launches += 1
+        return out
+
     def conj_copy(self, src, dst):
         self.handle.check(self.lib.isdf_conj_copy(self.h, _ptr(src), _ptr(dst), src.numel(), _stream()),
                           "isdf_conj_copy")

@@ -110,6 +110,14 @@ int isdf_phase_table(void* handle, const double* coords, const double* q_host, l
 int isdf_herk_scatter(void* handle, const void* b, long ldb, long strideB, int n, int k, double alpha,
                       const int* perm, long stridePerm, void* w, long ldw, long strideW, int batch, void* stream);
 
+/* Input producer for synthetic cells (fftisdf.py:350-352,367-370 pbc_eval_gto):
+ * out[k][g][mu] = sum_T e^{ik.T} N_mu P_mu(r_g-c_mu-T) exp(-alpha_mu |r_g-c_mu-T|^2).
+ * aos: device array of nao records {cx,cy,cz,alpha,norm, coef[3], pw[3][3] (int), nterm (int)} of
+ * isdf_ao_desc_bytes() bytes each; images [nimg][3]; kphase [nk][nimg] c128 = exp(i k.T). */
+int isdf_ao_desc_bytes(void);
+int isdf_eval_ao(void* handle, const double* coords, long npts, const void* aos, int nao, const double* images,
+                 int nimg, const void* kphase, int nk, void* out, void* stream);
+
 /* data movement: dst = conj(src) (time-reversal partner W_{-q} = W_q^*), and row gather
  * dst[z][i][:] = src[z][idx[z][i]][:] (zeros where idx < 0)  (fftisdf.py:388 x0[:, mask, :]). */
 int isdf_conj_copy(void* handle, const void* src, void* dst, long n, void* stream);

@@ -1,0 +1,262 @@
+// FP64 tensor-core DFT for awkward mesh lengths (large prime factors: 31, 37, 41, 43, 47, ...).
+//
+// PySCF's cutoff_to_mesh yields odd meshes whose prime factors are often large; a Stockham FFT then
+// degenerates to an O(n^2) direct DFT on the FP64 FMA pipe.  Here every 1-D transform of length n <= 48 is
+// a dense complex matrix product with the n x n DFT matrix, executed on the FP64 tensor pipe (DMMA.8x8x4)
+// with the same conflict-free LDS.128 fragment scheme as the GEMM engine (gemm_c128.cuh):
+//   * dft_zy_kernel: one CTA per (vector, x-plane); the n2 x n3 plane is staged once in shared memory,
+//     transformed along z then along y (the second product reads the first one's output as a K-contiguous
+//     operand, so no transpose is needed), and written back coalesced.  The e^{-iq.r} phase is fused into
+//     the load.
+//   * dft_x_kernel: lines along x for 64 consecutive (y,z) positions; the sqrt(v(q+G) vol)/ng weight is
+//     fused into the store.
+// Replaces pbctools.fft at /root/reference/fftisdf.py:113 (+ :99, :114-115) for such meshes.
+#include <math.h>
+#include <map>
+#include <vector>
+#include "common.cuh"
+
+namespace isdf {
+
+constexpr int DFT_MAXN = 48;
+constexpr int DFT_THREADS = 256;
+
+struct DftParams {
+  cplx* data; long ldv;        // [nvec][ldv]
+  int n1, n2, n3;
+  const cplx* w1; const cplx* w2; const cplx* w3;      // padded DFT matrices [np][np], W[i][k] = e^{-2 pi i ik/n}
+  long nwork;                  // planes (zy kernel) or line tiles (x kernel) in this launch
+  const cplx* pre;             // [ng] or null
+  const double* post;          // [ng] or null
+};
+
+__device__ __forceinline__ int pad8(int n) { return (n + 7) & ~7; }
+
+// copy the padded [np][np] DFT matrix from the plan into shared memory with row pitch ld
+__device__ __forceinline__ void fill_dft_matrix(cplx* W, const cplx* wg, int np, int ld) {
+  for (int w = threadIdx.x; w < np * np; w += DFT_THREADS) {
+    const int i = w / np, k = w - i * np;
+    W[i * ld + k] = wg[w];
+  }
+}
+
+// acc (8x8 complex tile, as re[2], im[2] per lane) += A(8 x K) * B(K x 8), MODE a*b
+template <bool A_KSLOW>
+__device__ __forceinline__ void tile_mma(double (&re)[2], double (&im)[2], const cplx* A, int lda, int m0,
+                                         const cplx* B, int ldb, int n0, int K, int g, int t) {
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const cplx a = A_KSLOW ? A[(k0 + t) * lda + m0 + g] : A[(m0 + g) * lda + k0 + t];
+    const cplx b = B[(k0 + t) * ldb + n0 + g];
+    dmma884(re[0], re[1], a.x, b.x);
+    dmma884(re[0], re[1], a.y, -b.y);
+    dmma884(im[0], im[1], a.x, b.y);
+    dmma884(im[0], im[1], a.y, b.x);
+  }
+}
+
+__global__ void __launch_bounds__(DFT_THREADS, 2) dft_zy_kernel(DftParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n2 = p.n2, n3 = p.n3;
+  const int n2p = pad8(n2), n3p = pad8(n3);
+  const int LDX = n2p + 2, LDY = n2p + 4, LDW3 = n3p + 2, LDW2 = n2p + 2;
+  cplx* Xs = reinterpret_cast<cplx*>(smem_raw);   // [n3p][LDX]   Xs[z][y]
+  cplx* Ys = Xs + n3p * LDX;                      // [n3p][LDY]   Ys[kz][y]
+  cplx* W3 = Ys + n3p * LDY;                      // [n3p][LDW3]  W3[z][kz]
+  cplx* W2 = W3 + n3p * LDW3;                     // [n2p][LDW2]  W2[y][ky]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  fill_dft_matrix(W3, p.w3, n3p, LDW3);
+  fill_dft_matrix(W2, p.w2, n2p, LDW2);
+  // persistent over planes: the DFT matrices stay in shared memory
+  for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+    const int plane = (int)(work % p.n1);
+    const long vec = work / p.n1;
+    const long poff = (long)plane * n2 * n3;
+    cplx* base = p.data + vec * p.ldv + poff;
+    // load plane transposed: Xs[z][y] = base[y*n3 + z] * pre ; zero padding
+    for (int w = tid; w < n3p * n2p; w += DFT_THREADS) {
+      const int y = w / n3p, z = w - y * n3p;   // z fastest: coalesced global reads
+      cplx v = make_double2(0.0, 0.0);
+      if (y < n2 && z < n3) {
+        v = base[y * n3 + z];
+        if (p.pre) v = cmul(v, p.pre[poff + y * n3 + z]);
+      }
+      Xs[z * LDX + y] = v;
+    }
+    __syncthreads();
+    // ---- pass 1: T[y][kz] = sum_z Xs[z][y] W3[z][kz]   -> Ys[kz][y]
+    {
+      const int mt_n = n2p >> 3, nt_n = n3p >> 3;
+      for (int w = warp; w < mt_n * nt_n; w += DFT_THREADS / 32) {
+        const int mt = w / nt_n, nt = w - mt * nt_n;
+        double re[2] = {0.0, 0.0}, im[2] = {0.0, 0.0};
+        tile_mma<true>(re, im, Xs, LDX, mt * 8, W3, LDW3, nt * 8, n3p, g, t);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) Ys[(nt * 8 + 2 * t + e) * LDY + mt * 8 + g] = make_double2(re[e], im[e]);
+      }
+    }
+    __syncthreads();
+    // ---- pass 2: out[kz][ky] = sum_y Ys[kz][y] W2[y][ky]   -> global [ky][kz]
+    {
+      const int mt_n = n3p >> 3, nt_n = n2p >> 3;
+      for (int w = warp; w < mt_n * nt_n; w += DFT_THREADS / 32) {
+        const int mt = w / nt_n, nt = w - mt * nt_n;
+        double re[2] = {0.0, 0.0}, im[2] = {0.0, 0.0};
+        tile_mma<false>(re, im, Ys, LDY, mt * 8, W2, LDW2, nt * 8, n2p, g, t);
+        const int kz = mt * 8 + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ky = nt * 8 + 2 * t + e;
+          if (kz < n3 && ky < n2) base[ky * n3 + kz] = make_double2(re[e], im[e]);
+        }
+      }
+    }
+    // Xs is rewritten by the next plane's load only after every warp finished pass 1 (barrier above); Ys is
+    // rewritten in the next pass 1, which comes after the next load's barrier.
+  }
+}
+
+constexpr int DFTX_LINES = 64;
+
+__global__ void __launch_bounds__(DFT_THREADS, 2) dft_x_kernel(DftParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n1 = p.n1;
+  const long n23 = (long)p.n2 * p.n3;
+  const int n1p = pad8(n1);
+  const int LDX = DFTX_LINES + 2, LDW = n1p + 2;
+  cplx* Xs = reinterpret_cast<cplx*>(smem_raw);   // [n1p][LDX]  Xs[x][l]
+  cplx* W1 = Xs + n1p * LDX;                      // [n1p][LDW]  W1[x][kx]
+  const int ntile = (int)((n23 + DFTX_LINES - 1) / DFTX_LINES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  fill_dft_matrix(W1, p.w1, n1p, LDW);
+  const int m0 = warp * 8;          // warp w owns lines 8w .. 8w+7 and all kx tiles (shared A fragment)
+  const int nt_n = n1p >> 3;
+  for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+    const int tile = (int)(work % ntile);
+    const long vec = work / ntile;
+    const long l0 = (long)tile * DFTX_LINES;
+    const int lcnt = (int)((n23 - l0 < DFTX_LINES) ? (n23 - l0) : DFTX_LINES);
+    cplx* base = p.data + vec * p.ldv + l0;
+    for (int w = tid; w < n1p * DFTX_LINES; w += DFT_THREADS) {
+      const int x = w / DFTX_LINES, l = w - x * DFTX_LINES;
+      cplx v = make_double2(0.0, 0.0);
+      if (x < n1 && l < lcnt) v = base[(long)x * n23 + l];
+      Xs[x * LDX + l] = v;
+    }
+    __syncthreads();
+    double re[DFT_MAXN / 8][2], im[DFT_MAXN / 8][2];
+#pragma unroll
+    for (int nt = 0; nt < DFT_MAXN / 8; ++nt) { re[nt][0] = re[nt][1] = im[nt][0] = im[nt][1] = 0.0; }
+    for (int k0 = 0; k0 < n1p; k0 += 4) {
+      const cplx a = Xs[(k0 + t) * LDX + m0 + g];
+#pragma unroll
+      for (int nt = 0; nt < DFT_MAXN / 8; ++nt) {
+        if (nt < nt_n) {
+          const cplx b = W1[(k0 + t) * LDW + nt * 8 + g];
+          dmma884(re[nt][0], re[nt][1], a.x, b.x);
+          dmma884(re[nt][0], re[nt][1], a.y, -b.y);
+          dmma884(im[nt][0], im[nt][1], a.x, b.y);
+          dmma884(im[nt][0], im[nt][1], a.y, b.x);
+        }
+      }
+    }
+    __syncthreads();   // all warps are done reading Xs: the next tile may overwrite it
+    const int l = m0 + g;
+#pragma unroll
+    for (int nt = 0; nt < DFT_MAXN / 8; ++nt) {
+      if (nt < nt_n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kx = nt * 8 + 2 * t + e;
+          if (kx < n1 && l < lcnt) {
+            cplx v = make_double2(re[nt][e], im[nt][e]);
+            const long off = (long)kx * n23 + l;
+            if (p.post) { const double wgt = p.post[l0 + off]; v.x *= wgt; v.y *= wgt; }
+            base[off] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// padded DFT matrices W[i][k] = exp(-2 pi i ik/n) ([np][np], zero padding), cached per (device, n)
+static std::map<std::pair<int, int>, cplx*>& dft_w_table() {
+  static std::map<std::pair<int, int>, cplx*> t;
+  return t;
+}
+
+static int get_w(Handle* h, int n, const cplx** out) {
+  auto key = std::make_pair(h->device, n);
+  auto it = dft_w_table().find(key);
+  if (it == dft_w_table().end()) {
+    const int np = (n + 7) & ~7;
+    std::vector<cplx> w((size_t)np * np, make_double2(0.0, 0.0));
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < n; ++k) {
+        const long j = ((long)i * k) % n;
+        const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+        w[(size_t)i * np + k] = make_double2((double)cosl(ang), (double)sinl(ang));
+      }
+    cplx* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(cplx) * w.size());
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpy(d, w.data(), sizeof(cplx) * w.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+    it = dft_w_table().insert(std::make_pair(key, d)).first;
+  }
+  *out = it->second;
+  return ISDF_OK;
+}
+
+}  // namespace isdf
+
+using namespace isdf;
+
+extern "C" void dft_release_plans_internal(int device) {
+  for (auto it = dft_w_table().begin(); it != dft_w_table().end();) {
+    if (it->first.first == device) { cudaFree(it->second); it = dft_w_table().erase(it); } else { ++it; }
+  }
+}
+
+// Same contract as isdf_fft3d_batched, every mesh axis in [2, 48].  Returns -2 (no launch) otherwise.
+extern "C" int isdf_dft3d_dmma(void* hv, void* data, long nvec, long ldv, const int* mesh, const void* pre_dev,
+                               const double* post_dev, void* stream) {
+  Handle* h = (Handle*)hv;
+  cudaStream_t st = (cudaStream_t)stream;
+  ISDF_CHECK_ARG(h, data && mesh, "null pointer");
+  const int n1 = mesh[0], n2 = mesh[1], n3 = mesh[2];
+  if (n1 < 2 || n2 < 2 || n3 < 2 || n1 > DFT_MAXN || n2 > DFT_MAXN || n3 > DFT_MAXN) return ISDF_ESIZE;
+  const long ng = (long)n1 * n2 * n3;
+  ISDF_CHECK_ARG(h, ldv >= ng, "ldv < prod(mesh)");
+  if (nvec <= 0) return ISDF_OK;
+  DftParams p;
+  p.data = (cplx*)data; p.ldv = ldv; p.n1 = n1; p.n2 = n2; p.n3 = n3;
+  p.pre = (const cplx*)pre_dev; p.post = post_dev;
+  int rc;
+  if ((rc = get_w(h, n1, &p.w1)) || (rc = get_w(h, n2, &p.w2)) || (rc = get_w(h, n3, &p.w3))) {
+    snprintf(h->err, sizeof(h->err), "dft matrix allocation failed (%d)", rc);
+    return rc;
+  }
+  const int n1p = (n1 + 7) & ~7, n2p = (n2 + 7) & ~7, n3p = (n3 + 7) & ~7;
+  const size_t sm_zy = (size_t)(n3p * (n2p + 2) + n3p * (n2p + 4) + n3p * (n3p + 2) + n2p * (n2p + 2)) * sizeof(cplx);
+  const size_t sm_x = (size_t)(n1p * (DFTX_LINES + 2) + n1p * (n1p + 2)) * sizeof(cplx);
+  ISDF_CHECK_ARG(h, sm_zy <= (size_t)h->max_smem_optin && sm_x <= (size_t)h->max_smem_optin, "mesh too large");
+  ISDF_CUDA(h, cudaFuncSetAttribute(dft_zy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_zy));
+  ISDF_CUDA(h, cudaFuncSetAttribute(dft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
+  // groups of vectors sized for L2 so that the x pass re-reads the zy pass's output from L2
+  long group = (long)(64.0 * 1024 * 1024 / ((double)ng * sizeof(cplx)));
+  if (group < 1) group = 1;
+  const long ntile = ((long)n2 * n3 + DFTX_LINES - 1) / DFTX_LINES;
+  for (long v0 = 0; v0 < nvec; v0 += group) {
+    const long nv = (nvec - v0 < group) ? (nvec - v0) : group;
+    p.data = (cplx*)data + v0 * ldv;
+    const long cap = (long)h->sm_count * 2 * 4;   // persistent CTAs: 2 per SM resident, 4 work items each at least
+    p.nwork = nv * n1;
+    dft_zy_kernel<<<(unsigned)((p.nwork < cap) ? p.nwork : cap), DFT_THREADS, sm_zy, st>>>(p);
+    ISDF_LAUNCH_CHECK(h);
+    p.nwork = nv * ntile;
+    dft_x_kernel<<<(unsigned)((p.nwork < cap) ? p.nwork : cap), DFT_THREADS, sm_x, st>>>(p);
+    ISDF_LAUNCH_CHECK(h);
+  }
+  return ISDF_OK;
+}

@@ -17,10 +17,22 @@
 
 namespace isdf {
 
-constexpr int FFT_THREADS = 128;
+#ifndef ISDF_FFT_THREADS
+#define ISDF_FFT_THREADS 128
+#endif
+#ifndef ISDF_FFT_OB
+#define ISDF_FFT_OB 4
+#endif
+#ifndef ISDF_FFT_LB
+#define ISDF_FFT_LB 4
+#endif
+#ifndef ISDF_FFT_T
+#define ISDF_FFT_T 32
+#endif
+constexpr int FFT_THREADS = ISDF_FFT_THREADS;
 constexpr int FFT_MAXSTAGES = 8;
-constexpr int FFT_OB = 4;   // outputs per thread (register blocking)
-constexpr int FFT_LB = 4;   // lines per thread
+constexpr int FFT_OB = ISDF_FFT_OB;   // outputs per thread (register blocking)
+constexpr int FFT_LB = ISDF_FFT_LB;   // lines per thread
 
 struct FftParams {
   cplx* data;        // in place
@@ -245,7 +257,7 @@ static int launch_pass(Handle* h, cplx* data, long nvec, long ldv, int n, long s
   p.nstages = pl->nstages;
   for (int i = 0; i < FFT_MAXSTAGES; ++i) p.radix[i] = (i < pl->nstages) ? pl->radix[i] : 1;
   p.tw = pl->tw; p.pre = pre; p.post = post;
-  int T = 32;
+  int T = ISDF_FFT_T;
   auto bytes = [&](int t) { return ((size_t)2 * n * ((t + FFT_LB) | 1) + n) * sizeof(cplx); };
   while (T > 1 && bytes(T) > (size_t)96 * 1024) T >>= 1;
   if (bytes(T) > (size_t)h->max_smem_optin) { snprintf(h->err, sizeof(h->err), "fft length %d too large", n); return ISDF_ESIZE; }

@@ -52,10 +52,12 @@ extern "C" int isdf_create(int device, void** out) {
 }
 
 extern "C" int isdf_fft_release_plans(void* hv);
+extern "C" void dft_release_plans_internal(int device);
 
 extern "C" int isdf_destroy(void* hv) {
   if (!hv) return ISDF_OK;
   isdf_fft_release_plans(hv);
+  dft_release_plans_internal(((Handle*)hv)->device);
   delete (Handle*)hv;
   return ISDF_OK;
 }

@@ -170,8 +170,21 @@ class IsdfOps:
         self.launches += 2 * (nP // TB)
 
     # ---- K6: batched 3-D FFT with fused phase / weight ----------------------------------------
-    def fft3d(self, data, mesh, pre=None, post=None, group_vecs=0, nvec=None, ldv=None):
-        """data: [..., ldv] rows of length prod(mesh) (row pitch ldv), transformed in place."""
+    @staticmethod
+    def _max_prime_factor(n):
+        f, p = 1, 2
+        while n > 1:
+            if n % p == 0:
+                f = p
+                n //= p
+            else:
+                p += 1
+        return f
+
+    def fft3d(self, data, mesh, pre=None, post=None, group_vecs=0, nvec=None, ldv=None, mode="auto"):
+        """data: [..., ldv] rows of length prod(mesh) (row pitch ldv), transformed in place.
+        mode: "stockham" (shared-memory Stockham FFT), "dmma" (tensor-core dense DFT, axes <= 48) or
+        "auto" (dmma whenever every axis is in [2, 48]: measured faster than Stockham on all such meshes)."""
         assert data.is_cuda and data.dtype == c128 and data.stride(-1) == 1
         ng = int(np.prod(mesh))
         if ldv is None:
@@ -179,6 +192,16 @@ class IsdfOps:
         if nvec is None:
             nvec = data.numel() // ldv
         m = (C.c_int * 3)(*[int(x) for x in mesh])
+        fits = all(2 <= int(x) <= 48 for x in mesh)
+        if mode == "auto":
+            mode = "dmma" if fits else "stockham"
+        if mode == "dmma":
+            assert fits, "dmma DFT needs every mesh axis in [2, 48]"
+            self.handle.check(self.lib.isdf_dft3d_dmma(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
+                                                       _stream()), "isdf_dft3d_dmma")
+            gv = max(1, int(64 * 1024 * 1024 / (ng * 16)))
+            self.launches += 2 * (-(-nvec // gv))
+            return
         self.handle.check(self.lib.isdf_fft3d_batched(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
                                                       int(group_vecs), _stream()), "isdf_fft3d_batched")
         gv = group_vecs if group_vecs > 0 else max(1, int(48 * 1024 * 1024 / (ng * 16)))

@@ -94,6 +94,11 @@ int isdf_trsm_sweeps(void* handle, const void* lfwd, const void* ubwd, void* t, 
 int isdf_fft3d_batched(void* handle, void* data, long nvec, long ldv, const int* mesh, const void* pre,
                        const double* post, long group_vecs, void* stream);
 int isdf_fft_release_plans(void* handle);
+/* Same contract as isdf_fft3d_batched for meshes with every axis in [2, 48]: each 1-D transform is a dense
+ * product with the n x n DFT matrix on the FP64 tensor pipe (for lengths with large prime factors, e.g. 31,
+ * 37, 41).  Returns -2 without launching when an axis is out of range. */
+int isdf_dft3d_dmma(void* handle, void* data, long nvec, long ldv, const int* mesh, const void* pre,
+                    const double* post, void* stream);
 
 /* Per-q tables of the Coulomb stage generated on the device:
  * fftisdf.py:114-115  get_coulG(cell, k=vq, mesh) (exxdiv=None, wrap_around=True) folded with vol/ngrid and

@@ -332,3 +332,24 @@ def test_device_ao_evaluation_matches_host(ops):
     got = cell.eval_ao_device(ops, coords, kpts).cpu().numpy()
     assert got.shape == ref.shape
     assert relerr(got, ref) < 1e-13
+
+
+@pytest.mark.parametrize("mesh", [[37, 37, 37], [31, 33, 37], [9, 10, 12], [48, 47, 41], [15, 15, 15], [2, 3, 5]])
+def test_dft3d_tensor_core_path(ops, mesh):
+    """Dense-DFT-on-DMMA path == numpy fftn (with fused phase and weight), incl. a padded vector pitch."""
+    rng = np.random.default_rng(16)
+    ng = int(np.prod(mesh))
+    nvec, ldv = 7, ng + 5
+    x = crand(rng, nvec, ldv)
+    pre = np.exp(1j * rng.uniform(0, 6.28, ng))
+    post = rng.uniform(0.1, 2.0, ng)
+    d = dev(x.copy())
+    ops.fft3d(d, mesh, pre=dev(pre), post=dev(post), nvec=nvec, ldv=ldv, mode="dmma")
+    got = d.cpu().numpy()
+    ref = np.fft.fftn((x[:, :ng] * pre).reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng) * post
+    assert relerr(got[:, :ng], ref) < 1e-13
+    assert np.array_equal(got[:, ng:], x[:, ng:])          # padding untouched
+    d = dev(x.copy())
+    ops.fft3d(d, mesh, nvec=nvec, ldv=ldv, mode="dmma")
+    ref = np.fft.fftn(x[:, :ng].reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng)
+    assert relerr(d.cpu().numpy()[:, :ng], ref) < 1e-13

@@ -47,6 +47,8 @@ SIGNATURES = {
     "isdf_fft3d_batched": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_long, c_void_p],
     "isdf_fft_release_plans": [c_void_p],
     "isdf_dft3d_dmma": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_void_p],
+    "isdf_dft3d_dmma_p2p": [c_void_p, C.POINTER(c_void_p), c_int, c_long, c_long, c_void_p, c_long, c_long, P_int,
+                            c_void_p, c_void_p, c_void_p],
     "isdf_ao_desc_bytes": [],
     "isdf_eval_ao": [c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "isdf_coulomb_weights": [c_void_p, C.POINTER(c_double), C.POINTER(c_double), P_int, c_double, c_void_p, c_void_p],

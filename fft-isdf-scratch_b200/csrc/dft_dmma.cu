@@ -26,6 +26,9 @@ struct DftParams {
   int n1, n2, n3;
   const cplx* w1; const cplx* w2; const cplx* w3;      // padded DFT matrices [np][np], W[i][k] = e^{-2 pi i ik/n}
   long nwork;                  // planes (zy kernel) or line tiles (x kernel) in this launch
+  // fused exchange over NVLink peer memory (world > 1): the zy kernel GATHERS its planes from the ranks'
+  // grid-column shards peer[r][(row0 + v) * ncol + (g - r*ncol)], the x kernel SCATTERS its output there.
+  cplx* peer[8]; int world; long ncol; long row0;
   const cplx* pre;             // [ng] or null
   const double* post;          // [ng] or null
 };
@@ -54,6 +57,7 @@ __device__ __forceinline__ void tile_mma(double (&re)[2], double (&im)[2], const
   }
 }
 
+template <bool GATHER>
 __global__ void __launch_bounds__(DFT_THREADS, 2) dft_zy_kernel(DftParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n2 = p.n2, n3 = p.n3;
@@ -77,7 +81,13 @@ __global__ void __launch_bounds__(DFT_THREADS, 2) dft_zy_kernel(DftParams p) {
       const int y = w / n3p, z = w - y * n3p;   // z fastest: coalesced global reads
       cplx v = make_double2(0.0, 0.0);
       if (y < n2 && z < n3) {
-        v = base[y * n3 + z];
+        if (GATHER) {
+          const long gidx = poff + y * n3 + z;
+          const int owner = (int)(gidx / p.ncol);
+          v = p.peer[owner][(p.row0 + vec) * p.ncol + (gidx - owner * p.ncol)];
+        } else {
+          v = base[y * n3 + z];
+        }
         if (p.pre) v = cmul(v, p.pre[poff + y * n3 + z]);
       }
       Xs[z * LDX + y] = v;
@@ -117,6 +127,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 2) dft_zy_kernel(DftParams p) {
 
 constexpr int DFTX_LINES = 64;
 
+template <bool SCATTER>
 __global__ void __launch_bounds__(DFT_THREADS, 2) dft_x_kernel(DftParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n1 = p.n1;
@@ -171,7 +182,13 @@ __global__ void __launch_bounds__(DFT_THREADS, 2) dft_x_kernel(DftParams p) {
             cplx v = make_double2(re[nt][e], im[nt][e]);
             const long off = (long)kx * n23 + l;
             if (p.post) { const double wgt = p.post[l0 + off]; v.x *= wgt; v.y *= wgt; }
-            base[off] = v;
+            if (SCATTER) {
+              const long gidx = l0 + off;
+              const int owner = (int)(gidx / p.ncol);
+              p.peer[owner][(p.row0 + vec) * p.ncol + (gidx - owner * p.ncol)] = v;
+            } else {
+              base[off] = v;
+            }
           }
         }
       }
@@ -218,20 +235,18 @@ extern "C" void dft_release_plans_internal(int device) {
   }
 }
 
-// Same contract as isdf_fft3d_batched, every mesh axis in [2, 48].  Returns -2 (no launch) otherwise.
-extern "C" int isdf_dft3d_dmma(void* hv, void* data, long nvec, long ldv, const int* mesh, const void* pre_dev,
-                               const double* post_dev, void* stream) {
-  Handle* h = (Handle*)hv;
-  cudaStream_t st = (cudaStream_t)stream;
-  ISDF_CHECK_ARG(h, data && mesh, "null pointer");
+static int dft3d_run(Handle* h, cplx* local, long nvec, long ldv, const int* mesh, const void* pre_dev,
+                     const double* post_dev, cplx* const* peer, int world, long ncol, long row0, cudaStream_t st) {
   const int n1 = mesh[0], n2 = mesh[1], n3 = mesh[2];
   if (n1 < 2 || n2 < 2 || n3 < 2 || n1 > DFT_MAXN || n2 > DFT_MAXN || n3 > DFT_MAXN) return ISDF_ESIZE;
   const long ng = (long)n1 * n2 * n3;
   ISDF_CHECK_ARG(h, ldv >= ng, "ldv < prod(mesh)");
   if (nvec <= 0) return ISDF_OK;
   DftParams p;
-  p.data = (cplx*)data; p.ldv = ldv; p.n1 = n1; p.n2 = n2; p.n3 = n3;
+  p.ldv = ldv; p.n1 = n1; p.n2 = n2; p.n3 = n3;
   p.pre = (const cplx*)pre_dev; p.post = post_dev;
+  p.world = world; p.ncol = ncol; p.row0 = row0;
+  for (int r = 0; r < 8; ++r) p.peer[r] = (peer && r < world) ? peer[r] : nullptr;
   int rc;
   if ((rc = get_w(h, n1, &p.w1)) || (rc = get_w(h, n2, &p.w2)) || (rc = get_w(h, n3, &p.w3))) {
     snprintf(h->err, sizeof(h->err), "dft matrix allocation failed (%d)", rc);
@@ -241,22 +256,58 @@ extern "C" int isdf_dft3d_dmma(void* hv, void* data, long nvec, long ldv, const 
   const size_t sm_zy = (size_t)(n3p * (n2p + 2) + n3p * (n2p + 4) + n3p * (n3p + 2) + n2p * (n2p + 2)) * sizeof(cplx);
   const size_t sm_x = (size_t)(n1p * (DFTX_LINES + 2) + n1p * (n1p + 2)) * sizeof(cplx);
   ISDF_CHECK_ARG(h, sm_zy <= (size_t)h->max_smem_optin && sm_x <= (size_t)h->max_smem_optin, "mesh too large");
-  ISDF_CUDA(h, cudaFuncSetAttribute(dft_zy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_zy));
-  ISDF_CUDA(h, cudaFuncSetAttribute(dft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
+  const bool p2p = peer != nullptr;
+  if (p2p) {
+    ISDF_CUDA(h, cudaFuncSetAttribute(dft_zy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_zy));
+    ISDF_CUDA(h, cudaFuncSetAttribute(dft_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
+  } else {
+    ISDF_CUDA(h, cudaFuncSetAttribute(dft_zy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_zy));
+    ISDF_CUDA(h, cudaFuncSetAttribute(dft_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
+  }
   // groups of vectors sized for L2 so that the x pass re-reads the zy pass's output from L2
   long group = (long)(64.0 * 1024 * 1024 / ((double)ng * sizeof(cplx)));
   if (group < 1) group = 1;
   const long ntile = ((long)n2 * n3 + DFTX_LINES - 1) / DFTX_LINES;
+  const long cap = (long)h->sm_count * 2 * 4;   // persistent CTAs: 2 per SM resident, >= 4 work items each
   for (long v0 = 0; v0 < nvec; v0 += group) {
     const long nv = (nvec - v0 < group) ? (nvec - v0) : group;
-    p.data = (cplx*)data + v0 * ldv;
-    const long cap = (long)h->sm_count * 2 * 4;   // persistent CTAs: 2 per SM resident, 4 work items each at least
+    p.data = local + v0 * ldv;
+    p.row0 = row0 + v0;
     p.nwork = nv * n1;
-    dft_zy_kernel<<<(unsigned)((p.nwork < cap) ? p.nwork : cap), DFT_THREADS, sm_zy, st>>>(p);
+    const unsigned g1 = (unsigned)((p.nwork < cap) ? p.nwork : cap);
+    if (p2p) dft_zy_kernel<true><<<g1, DFT_THREADS, sm_zy, st>>>(p);
+    else dft_zy_kernel<false><<<g1, DFT_THREADS, sm_zy, st>>>(p);
     ISDF_LAUNCH_CHECK(h);
     p.nwork = nv * ntile;
-    dft_x_kernel<<<(unsigned)((p.nwork < cap) ? p.nwork : cap), DFT_THREADS, sm_x, st>>>(p);
+    const unsigned g2 = (unsigned)((p.nwork < cap) ? p.nwork : cap);
+    if (p2p) dft_x_kernel<true><<<g2, DFT_THREADS, sm_x, st>>>(p);
+    else dft_x_kernel<false><<<g2, DFT_THREADS, sm_x, st>>>(p);
     ISDF_LAUNCH_CHECK(h);
   }
   return ISDF_OK;
+}
+
+// Same contract as isdf_fft3d_batched, every mesh axis in [2, 48].  Returns -2 (no launch) otherwise.
+extern "C" int isdf_dft3d_dmma(void* hv, void* data, long nvec, long ldv, const int* mesh, const void* pre_dev,
+                               const double* post_dev, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, data && mesh, "null pointer");
+  return dft3d_run(h, (cplx*)data, nvec, ldv, mesh, pre_dev, post_dev, nullptr, 1, 0, 0, (cudaStream_t)stream);
+}
+
+// Multi-GPU variant with the all-to-all exchanges fused into the transform over NVLink peer memory.
+// peers: HOST array of `world` (<= 8) device pointers, peers[r] = rank r's grid-column shard
+// [rows][ncol] (peer-mapped, e.g. torch symmetric memory); this rank transforms the `nvec` vectors stored in
+// rows row0 .. row0+nvec-1 of every shard: the z/y kernel gathers each plane from the owning ranks, the
+// result stays in `work` ([nvec][ldv >= ng], local), the x kernel scatters its output (times `post`) back
+// into the shards.  Callers must barrier across ranks before (shards complete) and after (scatter visible).
+extern "C" int isdf_dft3d_dmma_p2p(void* hv, void* const* peers, int world, long ncol, long row0, void* work,
+                                   long nvec, long ldv, const int* mesh, const void* pre_dev,
+                                   const double* post_dev, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, peers && work && mesh, "null pointer");
+  ISDF_CHECK_ARG(h, world >= 1 && world <= 8 && ncol >= 1 && row0 >= 0, "world/ncol/row0");
+  ISDF_CHECK_ARG(h, (long)world * ncol >= (long)mesh[0] * mesh[1] * mesh[2], "shards do not cover the grid");
+  return dft3d_run(h, (cplx*)work, nvec, ldv, mesh, pre_dev, post_dev, (cplx* const*)peers, world, ncol, row0,
+                   (cudaStream_t)stream);
 }

@@ -216,7 +216,20 @@ def build(df_obj):
     ngrid = coord.shape[0]
     g_lo, g_hi, ncol = sharding.col_shard(ngrid, world, rank)
     _log(df_obj, "nkpt = %d, ngrid = %d, nip = %d", nkpt, ngrid, nip)
-    theta = torch.zeros((nq, nipP, ncol), dtype=torch.complex128, device=dev)  # Y^T, then Theta, then B
+    # Y^T, then Theta, then B (in place).  Multi-GPU with a tensor-core-DFT mesh: the buffer lives in NVLink
+    # peer-mapped memory so that the FFT kernels gather/scatter it directly (no all-to-all, no permute copies).
+    p2p = world > 1 and all(2 <= m <= 48 for m in mesh) and getattr(df_obj, "exchange", "p2p") == "p2p"
+    if p2p:
+        cache = df_obj.__dict__.setdefault("_peer_cache", {})   # symmetric allocations are reused across builds
+        key = (nq, nipP, ncol)
+        if key not in cache:
+            cache.clear()
+            cache[key] = sharding.PeerBuffer(key, dev, comm)
+        peerbuf = cache[key]
+        theta = peerbuf.tensor
+        theta.zero_()
+    else:
+        theta = torch.zeros((nq, nipP, ncol), dtype=torch.complex128, device=dev)
     blksize = int(df_obj.blksize)
     fx_k = None
     tab = getattr(df_obj, "_ao_tables", None)
@@ -265,23 +278,37 @@ def build(df_obj):
 
     # ---- D. Coulomb kernel                                                       :96-122
     vol = float(pcell.vol)
-    vecs = sharding.to_vector_layout(theta, comm)            # [nq][nipP/world][world*ncol]
-    if world > 1:
-        del theta
-    nv, ldv = vecs.shape[1], vecs.shape[2]
     coord_d = _to_dev(ops, coord, pinned=False)
     stats["h2d_bytes"] += coord.nbytes
     bvec = pbc_tools.reciprocal_vectors(a)
     kscaled = pbc_tools.get_scaled_kpts(a, vk)
     fq_d = torch.empty((ngrid,), dtype=torch.complex128, device=dev)
     wgt_d = torch.empty((ngrid,), dtype=torch.float64, device=dev)
-    for s, q in enumerate(qind):                                              # :97
-        ops.phase_table(coord_d, vk[q], fq_d)                                 # :99   fq = exp(-i r.q)
-        ops.coulomb_weights(bvec, kscaled[q], mesh, vol, wgt_d)               # :114-115 sqrt(coulG vol)/ng
-        ops.fft3d(vecs[s], mesh, pre=fq_d, post=wgt_d, nvec=nv, ldv=ldv)      # :113-115
-    mark("fft")
-    theta = sharding.to_column_layout(vecs, comm)            # [nq][nipP][ncol]
-    del vecs
+    if p2p:
+        # fused exchange: each rank transforms its nipP/world vectors of every q, reading the planes from and
+        # writing the result to the ranks' column shards over NVLink inside the DFT kernels
+        nv = nipP // world
+        work = torch.empty((nv, ngrid), dtype=torch.complex128, device=dev)
+        peerbuf.barrier()                                    # every rank's Theta shard is complete
+        for s, q in enumerate(qind):                                              # :97
+            ops.phase_table(coord_d, vk[q], fq_d)                                 # :99
+            ops.coulomb_weights(bvec, kscaled[q], mesh, vol, wgt_d)               # :114-115
+            ops.dft3d_p2p(peerbuf.ptrs, ncol, s * nipP + rank * nv, work, nv, mesh, pre=fq_d, post=wgt_d)
+        peerbuf.barrier()                                    # all scatters have landed
+        del work
+        mark("fft")
+    else:
+        vecs = sharding.to_vector_layout(theta, comm)            # [nq][nipP/world][world*ncol]
+        if world > 1:
+            del theta
+        nv, ldv = vecs.shape[1], vecs.shape[2]
+        for s, q in enumerate(qind):                                              # :97
+            ops.phase_table(coord_d, vk[q], fq_d)                                 # :99   fq = exp(-i r.q)
+            ops.coulomb_weights(bvec, kscaled[q], mesh, vol, wgt_d)               # :114-115 sqrt(coulG vol)/ng
+            ops.fft3d(vecs[s], mesh, pre=fq_d, post=wgt_d, nvec=nv, ldv=ldv)      # :113-115
+        mark("fft")
+        theta = sharding.to_column_layout(vecs, comm)            # [nq][nipP][ncol]
+        del vecs
     wslot = torch.zeros((nq, nip, nip), dtype=torch.complex128, device=dev)
     nrow = min(nip, nipP)
     ops.herk_strided(theta, ncol, nipP * ncol, nrow, ncol, 1.0, piv_q, nip, wslot, nip, nip * nip, nq)   # :121

@@ -207,6 +207,18 @@ class IsdfOps:
         gv = group_vecs if group_vecs > 0 else max(1, int(48 * 1024 * 1024 / (ng * 16)))
         self.launches += 3 * (-(-nvec // gv))
 
+    def dft3d_p2p(self, peer_ptrs, ncol, row0, work, nvec, mesh, pre=None, post=None):
+        """Tensor-core DFT with the all-to-all exchanges fused over NVLink peer memory (see the C header)."""
+        world = len(peer_ptrs)
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        m = (C.c_int * 3)(*[int(x) for x in mesh])
+        self.handle.check(self.lib.isdf_dft3d_dmma_p2p(self.h, arr, world, int(ncol), int(row0), _ptr(work), int(nvec),
+                                                       work.shape[-1], m, _ptr(pre), _ptr(post), _stream()),
+                          "isdf_dft3d_dmma_p2p")
+        ng = int(np.prod(mesh))
+        gv = max(1, int(64 * 1024 * 1024 / (ng * 16)))
+        self.launches += 2 * (-(-nvec // gv))
+
     # ---- K7: W = alpha * B B^H, scattered through perm -------------------------------------------
     def herk(self, b, alpha=1.0, perm=None, out=None):
         _chk(b, c128)

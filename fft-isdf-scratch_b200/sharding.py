@@ -102,3 +102,22 @@ def broadcast_(t, src=0, group=None):
     if world > 1:
         dist.broadcast(torch.view_as_real(t) if t.is_complex() else t, src=src, group=group)
     return t
+
+
+class PeerBuffer:
+    """A complex128 tensor in NVLink peer-mapped (symmetric) memory: every rank can load/store every other
+    rank's copy from inside a kernel.  Thin wrapper over torch.distributed._symmetric_memory."""
+
+    def __init__(self, shape, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        self.raw = symm_mem.empty(numel * 2, dtype=torch.float64, device=device)
+        self.handle = symm_mem.rendezvous(self.raw, group.group_name if hasattr(group, "group_name") else group)
+        self.tensor = torch.view_as_complex(self.raw.view(-1, 2)).view(*shape)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def barrier(self):
+        """All ranks' prior work on the current stream is visible to every peer afterwards."""
+        self.handle.barrier()

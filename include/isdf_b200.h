@@ -99,6 +99,14 @@ int isdf_fft_release_plans(void* handle);
  * 37, 41).  Returns -2 without launching when an axis is out of range. */
 int isdf_dft3d_dmma(void* handle, void* data, long nvec, long ldv, const int* mesh, const void* pre,
                     const double* post, void* stream);
+/* Multi-GPU form with both all-to-all exchanges fused into the transform over NVLink peer memory.
+ * peers: HOST array of `world` (<= 8) peer-mapped device pointers, peers[r] = rank r's grid-column shard
+ * [rows][ncol] (rank r owns grid points [r*ncol, (r+1)*ncol)).  This rank transforms the nvec vectors in rows
+ * row0 .. row0+nvec-1 of every shard: the z/y kernel GATHERS each x-plane from the owning ranks (P2P loads), the
+ * intermediate stays in `work` ([nvec][ldv >= ng], local), the x kernel SCATTERS post[G]*result into the shards
+ * (P2P stores).  The caller barriers across ranks before (shards complete) and after (scatter visible). */
+int isdf_dft3d_dmma_p2p(void* handle, void* const* peers, int world, long ncol, long row0, void* work, long nvec,
+                        long ldv, const int* mesh, const void* pre, const double* post, void* stream);
 
 /* Per-q tables of the Coulomb stage generated on the device:
  * fftisdf.py:114-115  get_coulG(cell, k=vq, mesh) (exxdiv=None, wrap_around=True) folded with vol/ngrid and

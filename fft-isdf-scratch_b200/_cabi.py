@@ -29,6 +29,13 @@ SIGNATURES = {
                         c_int, c_int, c_int, c_int, c_void_p],
     "isdf_ktransform_square_rows": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_long, c_int, c_int,
                                     P_int, c_void_p, c_int, c_void_p, c_void_p, c_long, c_void_p, c_void_p],
+    "isdf_ktransform_rows_ex": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_long, c_int, c_int,
+                                P_int, c_void_p, c_int, c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_long,
+                                c_long, c_double, c_void_p],
+    "isdf_gemm_hn": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_long, c_long,
+                     c_int, c_int, c_int, c_int, c_void_p],
+    "isdf_rowdot_conj_sum": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p],
+    "isdf_scale_rows": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "isdf_herk_scatter": [c_void_p, c_void_p, c_long, c_long, c_int, c_int, c_double, c_void_p, c_long, c_void_p,
                           c_long, c_long, c_int, c_void_p],
     "isdf_gemm_nn": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_long, c_long,

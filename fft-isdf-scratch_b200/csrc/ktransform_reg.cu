@@ -18,6 +18,9 @@ struct KtRegParams {
   const int* qslot;                  // [nk] or null
   const int* rowmap; long rowmap_sq; // [nslot][nrows] or null
   double* diag;
+  // mode 0: y = s*s (metric / right-hand side).  mode 1: y = scale * Re(s) * table[R][r][c] (exchange build,
+  // fftisdf.py:215-223).  mode 2: write scale * Re(s) as a real table [R][r][c] and stop (fftisdf.py:205-207).
+  int mode; const double* table; long tab_sk; long tab_sr; double scale;
 };
 
 template <int N, int STRIDE, int NK, int AX, bool CONJ>
@@ -63,9 +66,12 @@ __global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
     for (int k = 0; k < NK; ++k) {
       mx_im = fmax(mx_im, fabs(x[k].y));
       mx_re = fmax(mx_re, fabs(x[k].x));
-      x[k] = make_double2(x[k].x * x[k].x, 0.0);
+      if (p.mode == 0) x[k] = make_double2(x[k].x * x[k].x, 0.0);
+      else if (p.mode == 1) x[k] = make_double2(p.scale * x[k].x * p.table[(long)k * p.tab_sk + (long)r * p.tab_sr + c], 0.0);
+      else reinterpret_cast<double*>(p.out)[(long)k * p.out_sq + (long)r * p.out_sr + p.out_c0 + c] = p.scale * x[k].x;
     }
-    if (p.conj2) {
+    if (p.mode == 2) {
+    } else if (p.conj2) {
       dft_axis<N3, 1, NK, 2, true>(x);
       dft_axis<N2, N3, NK, 1, true>(x);
       dft_axis<N1, N2 * N3, NK, 0, true>(x);
@@ -76,6 +82,7 @@ __global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
     }
 #pragma unroll
     for (int q = 0; q < NK; ++q) {
+      if (p.mode == 2) continue;
       const int slot = p.qslot ? p.qslot[q] : q;
       if (slot < 0) continue;
       int row = r;
@@ -153,11 +160,20 @@ __global__ void __launch_bounds__(128) ktransform_split_kernel(KtRegParams p) {
   for (int l = 0; l < NL; ++l) {
     mx_im = fmax(mx_im, fabs(x[l].y));
     mx_re = fmax(mx_re, fabs(x[l].x));
-    x[l] = make_double2(x[l].x * x[l].x, 0.0);
+    if (p.mode == 0) {
+      x[l] = make_double2(x[l].x * x[l].x, 0.0);
+    } else if (p.mode == 1) {
+      const double tv = valid ? p.table[(long)kof(l) * p.tab_sk + (long)r * p.tab_sr + c] : 0.0;
+      x[l] = make_double2(p.scale * x[l].x * tv, 0.0);
+    } else if (valid) {
+      reinterpret_cast<double*>(p.out)[(long)kof(l) * p.out_sq + (long)r * p.out_sr + p.out_c0 + c] = p.scale * x[l].x;
+    }
   }
-  if (p.conj2) kt_split_transform<N1, N2, N3, SA, true>(x, sub, lane);
-  else kt_split_transform<N1, N2, N3, SA, false>(x, sub, lane);
-  if (valid) {
+  if (p.mode != 2) {
+    if (p.conj2) kt_split_transform<N1, N2, N3, SA, true>(x, sub, lane);
+    else kt_split_transform<N1, N2, N3, SA, false>(x, sub, lane);
+  }
+  if (valid && p.mode != 2) {
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const int q = kof(l);
@@ -207,10 +223,11 @@ using namespace isdf;
 
 // Returns ISDF_ESIZE (-2) without launching when the mesh has no register instantiation; the caller
 // then uses isdf_ktransform_square (shared-memory kernel).
-extern "C" int isdf_ktransform_square_rows(void* hv, const void* in, long in_sk, long in_sr, void* out, long out_sq,
-                                           long out_sr, long out_c0, int nrows, int ncols, const int* kmesh,
-                                           const void* uaxes_host, int conj2, const int* qslot, const int* rowmap,
-                                           long rowmap_sq, double* diag, void* stream) {
+extern "C" int isdf_ktransform_rows_ex(void* hv, const void* in, long in_sk, long in_sr, void* out, long out_sq,
+                                       long out_sr, long out_c0, int nrows, int ncols, const int* kmesh,
+                                       const void* uaxes_host, int conj2, const int* qslot, const int* rowmap,
+                                       long rowmap_sq, double* diag, int mode, const double* table, long tab_sk,
+                                       long tab_sr, double scale, void* stream) {
   Handle* h = (Handle*)hv;
   cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, in && out && kmesh && uaxes_host, "null pointer");
@@ -225,6 +242,8 @@ extern "C" int isdf_ktransform_square_rows(void* hv, const void* in, long in_sk,
   p.out = (cplx*)out; p.out_sq = out_sq; p.out_sr = out_sr; p.out_c0 = out_c0;
   p.nrows = nrows; p.ncols = ncols; p.conj2 = conj2;
   p.qslot = qslot; p.rowmap = rowmap; p.rowmap_sq = rowmap_sq; p.diag = diag;
+  ISDF_CHECK_ARG(h, mode >= 0 && mode <= 2 && (mode != 1 || table != nullptr), "mode/table");
+  p.mode = mode; p.table = table; p.tab_sk = tab_sk; p.tab_sr = tab_sr; p.scale = scale;
   cudaError_t e = cudaSuccess;
   bool hit = false;
   KT_CASE(1, 1, 1) KT_CASE(1, 1, 2) KT_CASE(1, 2, 1) KT_CASE(2, 1, 1) KT_CASE(1, 2, 2) KT_CASE(2, 1, 2)
@@ -241,4 +260,12 @@ extern "C" int isdf_ktransform_square_rows(void* hv, const void* in, long in_sk,
   if (!hit) return ISDF_ESIZE;
   ISDF_CUDA(h, e);
   return ISDF_OK;
+}
+
+extern "C" int isdf_ktransform_square_rows(void* hv, const void* in, long in_sk, long in_sr, void* out, long out_sq,
+                                           long out_sr, long out_c0, int nrows, int ncols, const int* kmesh,
+                                           const void* uaxes_host, int conj2, const int* qslot, const int* rowmap,
+                                           long rowmap_sq, double* diag, void* stream) {
+  return isdf_ktransform_rows_ex(hv, in, in_sk, in_sr, out, out_sq, out_sr, out_c0, nrows, ncols, kmesh, uaxes_host,
+                                 conj2, qslot, rowmap, rowmap_sq, diag, 0, nullptr, 0, 0, 1.0, stream);
 }

@@ -23,6 +23,40 @@ __global__ void gather_rows_kernel(const cplx* __restrict__ src, long lds, long 
     d[c] = (r >= 0) ? s[c] : make_double2(0.0, 0.0);
 }
 
+// out[i] = scale * sum_z sum_n y[z][i][n] * conj(x[z][i][n])          (fftisdf.py:155-156, rho_I)
+__global__ void rowdot_conj_sum_kernel(const cplx* __restrict__ y, const cplx* __restrict__ x, int nz, int nrows,
+                                       int ncols, double scale, cplx* __restrict__ out) {
+  const int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= nrows) return;
+  double ar = 0.0, ai = 0.0;
+  for (int z = 0; z < nz; ++z) {
+    const cplx* yr = y + ((long)z * nrows + i) * ncols;
+    const cplx* xr = x + ((long)z * nrows + i) * ncols;
+    for (int n = lane; n < ncols; n += 32) {
+      const cplx a = yr[n], b = xr[n];
+      ar += a.x * b.x + a.y * b.y;
+      ai += a.y * b.x - a.x * b.y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+  }
+  if (lane == 0) out[i] = make_double2(scale * ar, scale * ai);
+}
+
+// out[z][i][n] = v[i] * x[z][i][n]                                       (fftisdf.py:166, diag(v) X_k)
+__global__ void scale_rows_kernel(const cplx* __restrict__ x, const cplx* __restrict__ v, int nrows, int ncols,
+                                  long total, cplx* __restrict__ out) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+    const int i = (int)((w / ncols) % nrows);
+    out[w] = cmul(v[i], x[w]);
+  }
+}
+
 }  // namespace isdf
 
 using namespace isdf;
@@ -152,6 +186,46 @@ extern "C" int isdf_gemm_nn(void* hv, const void* a, long lda, long strideA, con
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
   p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
   ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
+// c[z][i][j] = sum_l conj(a[z][l][i]) * b[z][l][j]   (A^H B; a [k][m], b [k][n] row-major)   fftisdf.py:166, :225
+extern "C" int isdf_gemm_hn(void* hv, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                            void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, a && b && c, "null pointer");
+  ISDF_CHECK_ARG(h, m >= 0 && n >= 0 && k >= 0 && batch >= 0 && batch <= 65535, "shape");
+  GemmParams p;
+  p.A = (const cplx*)a; p.lda = lda; p.strideA = strideA;
+  p.B = (const cplx*)b; p.ldb = ldb; p.strideB = strideB;
+  p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
+  p.M = m; p.N = n; p.K = k;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  ISDF_CUDA(h, (launch_gemm<128, 64, true, true, MODE_CONJA, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
+extern "C" int isdf_rowdot_conj_sum(void* hv, const void* y, const void* x, int nz, int nrows, int ncols, double scale,
+                                    void* out, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, y && x && out && nz >= 1 && nrows >= 1 && ncols >= 1, "args");
+  rowdot_conj_sum_kernel<<<(nrows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const cplx*)y, (const cplx*)x, nz, nrows,
+                                                                         ncols, scale, (cplx*)out);
+  ISDF_LAUNCH_CHECK(h);
+  return ISDF_OK;
+}
+
+extern "C" int isdf_scale_rows(void* hv, const void* x, const void* v, int nz, int nrows, int ncols, void* out,
+                               void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, x && v && out && nz >= 1 && nrows >= 1 && ncols >= 1, "args");
+  const long total = (long)nz * nrows * ncols;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  scale_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const cplx*)x, (const cplx*)v, nrows, ncols,
+                                                                        total, (cplx*)out);
+  ISDF_LAUNCH_CHECK(h);
   return ISDF_OK;
 }
 

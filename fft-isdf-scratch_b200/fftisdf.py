@@ -352,6 +352,11 @@ def get_j_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=Non
     assert df_obj._x.shape == (nkpt, nip, nao)
     assert df_obj._w0.shape == (nip, nip)
     assert kpts_band is None, "kpts_band is not supported (fftisdf.py:164)"
+    if _jk_device_ok(df_obj):
+        vj_kpts = get_j_kpts_device(df_obj, dms)
+        if abs(kpts).max() < 1e-9:
+            vj_kpts = vj_kpts.real
+        return vj_kpts.reshape(dm_kpts.shape)
     rho = numpy.einsum("kIm,kIn,xkmn->xI", df_obj._x, df_obj._x.conj(), dms, optimize=True)
     rho *= 1.0 / nkpt
     v = numpy.einsum("IJ,xJ->xI", df_obj._w0, rho, optimize=True)
@@ -377,6 +382,8 @@ def get_k_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=Non
     nip = df_obj._x.shape[1]
     assert df_obj._x.shape == (nkpt, nip, nao)
     assert df_obj._wq.shape == (nkpt, nip, nip)
+    if _jk_device_ok(df_obj):
+        return get_k_kpts_device(df_obj, dms).reshape(dm_kpts.shape)
     ws = phase @ df_obj._wq.reshape(nkpt, -1)
     ws = ws.reshape(nkpt, nip, nip)
     ws = ws.real * numpy.sqrt(nkpt)
@@ -391,6 +398,56 @@ def get_k_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=Non
         vk_kpts.append([x.conj().T @ v @ x for x, v in zip(df_obj._x, vk)])
     vk_kpts = numpy.asarray(vk_kpts).reshape(nset, nkpt, nao, nao)
     return vk_kpts.reshape(dm_kpts.shape)
+
+
+def _jk_device_ok(df_obj):
+    return (getattr(df_obj, "jk_on_device", True) and getattr(df_obj, "_x_dev", None) is not None
+            and max(df_obj.kmesh) <= 4)
+
+
+def get_j_kpts_device(df_obj, dms):
+    """fftisdf.py:155-166 on the device.  dms: [nset, nk, nao, nao] numpy -> vj same shape (numpy)."""
+    ops = df_obj._ops
+    x = df_obj._x_dev
+    nk, nip, nao = x.shape
+    w0 = df_obj._wq_dev[0:1].contiguous()
+    out = []
+    for dm in dms:
+        d = torch.from_numpy(numpy.ascontiguousarray(dm)).to(ops.device)
+        y = ops.gemm_nn(x, d)                                             # Y_k = X_k D_k
+        rho = ops.rowdot_conj_sum(y, x, 1.0 / nk)                         # :155-156
+        v = ops.gemm_nn(w0, rho.reshape(1, nip, 1).contiguous())          # :159  v = W_0 rho
+        xv = ops.scale_rows(x, v.reshape(nip).contiguous())               # diag(v) X_k
+        out.append(ops.gemm_hn(x, xv).cpu().numpy())                      # :166  X_k^H diag(v) X_k
+    return numpy.asarray(out)
+
+
+def get_k_kpts_device(df_obj, dms):
+    """fftisdf.py:204-227 on the device (k<->R transforms with the register k-transform kernels)."""
+    ops = df_obj._ops
+    x = df_obj._x_dev
+    wq = df_obj._wq_dev
+    nk, nip, nao = x.shape
+    kmesh = df_obj.kmesh
+    uax_h = ops.pack_uaxes_host(kmesh)
+    diag = torch.zeros(2, dtype=torch.float64, device=ops.device)
+    ws = torch.empty((nk, nip, nip), dtype=torch.float64, device=ops.device)
+    ok = ops.ktransform_rows_ex(wq, nip * nip, nip, ws, nip * nip, nip, 0, nip, nip, kmesh, uax_h, 0, mode=2,
+                                scale=float(numpy.sqrt(nk)))              # :205-207 ws = Re(phase @ wq) sqrt(nk)
+    assert ok
+    out = []
+    for dm in dms:
+        d = torch.from_numpy(numpy.ascontiguousarray(dm)).to(ops.device)
+        y = ops.gemm_nn(x, d)                                             # Y_k = X_k D_k
+        g = ops.gram_conja(x, y)                                          # g[k][I][J] = rhok[k][J][I] * nk   (:211)
+        vk_ip = torch.empty((nk, nip, nip), dtype=torch.complex128, device=ops.device)
+        ops.ktransform_rows_ex(g, nip * nip, nip, vk_ip, nip * nip, nip, 0, nip, nip, kmesh, uax_h, 0, mode=1,
+                               table=ws, tab_sk=nip * nip, tab_sr=nip, scale=1.0 / nk, diag=diag)   # :212-223
+        z = ops.gemm_nn(vk_ip, x)                                         # vk X_k
+        out.append(ops.gemm_hn(x, z).cpu().numpy())                       # :225  X_k^H vk X_k
+    dd = diag.cpu().numpy()
+    assert dd[0] < 1e-10 * max(1.0, dd[1]), "abs(rhos.imag).max() = %g" % dd[0]   # :216
+    return numpy.asarray(out)
 
 
 class InterpolativeSeparableDensityFitting(_Base):

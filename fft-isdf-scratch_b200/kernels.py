@@ -125,6 +125,49 @@ class IsdfOps:
         self.launches += 1
         return True
 
+    def ktransform_rows_ex(self, vin, in_sk, in_sr, out, out_sq, out_sr, out_c0, nrows, ncols, kmesh, uaxes_host, conj2,
+                           mode, table=None, tab_sk=0, tab_sr=0, scale=1.0, diag=None):
+        """mode 1: scale*Re(P v)*table then second transform; mode 2: write scale*Re(P v) as a real table."""
+        km = (C.c_int * 3)(*[int(x) for x in kmesh])
+        rc = self.lib.isdf_ktransform_rows_ex(
+            self.h, _ptr(vin), in_sk, in_sr, _ptr(out), out_sq, out_sr, out_c0, nrows, ncols, km,
+            C.c_void_p(uaxes_host.ctypes.data), int(conj2), None, None, 0, _ptr(diag), int(mode), _ptr(table),
+            tab_sk, tab_sr, float(scale), _stream())
+        if rc == -2:
+            return False
+        self.handle.check(rc, "isdf_ktransform_rows_ex")
+        self.launches += 1
+        return True
+
+    def gemm_hn(self, a, b):
+        """out[z] = a[z]^H @ b[z]; a [batch,k,m], b [batch,k,n]."""
+        _chk(a, c128), _chk(b, c128)
+        batch, k, m = a.shape
+        n = b.shape[2]
+        out = torch.empty((batch, m, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gemm_hn(self.h, _ptr(a), m, k * m, _ptr(b), n, k * n, _ptr(out), n, m * n,
+                                                m, n, k, batch, _stream()), "isdf_gemm_hn")
+        self.launches += 1
+        return out
+
+    def rowdot_conj_sum(self, y, x, scale):
+        _chk(y, c128), _chk(x, c128)
+        nz, nrows, ncols = x.shape
+        out = torch.empty((nrows,), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_rowdot_conj_sum(self.h, _ptr(y), _ptr(x), nz, nrows, ncols, float(scale),
+                                                        _ptr(out), _stream()), "isdf_rowdot_conj_sum")
+        self.launches += 1
+        return out
+
+    def scale_rows(self, x, v):
+        _chk(x, c128), _chk(v, c128)
+        nz, nrows, ncols = x.shape
+        out = torch.empty_like(x)
+        self.handle.check(self.lib.isdf_scale_rows(self.h, _ptr(x), _ptr(v), nz, nrows, ncols, _ptr(out), _stream()),
+                          "isdf_scale_rows")
+        self.launches += 1
+        return out
+
     def pack_uaxes_host(self, kmesh):
         from .pbc_tools import get_phase_axes
         u = np.zeros((3, KT_NMAX, KT_NMAX), dtype=np.complex128)

@@ -79,6 +79,25 @@ int isdf_ktransform_square_rows(void* handle, const void* in, long in_sk, long i
                                 const void* uaxes_host, int conj2, const int* qslot, const int* rowmap,
                                 long rowmap_sq, double* diag, void* stream);
 
+/* General form of the register k-transform: mode 0 = square (as above); mode 1 = multiply scale*Re(s) by a real
+ * R-space table[R*tab_sk + r*tab_sr + c] before the second transform (exchange: vs = ws * rhos^T, fftisdf.py:215-223);
+ * mode 2 = write scale*Re(s) as a real table out[R*out_sq + r*out_sr + out_c0 + c] (doubles) and stop
+ * (ws = Re(phase @ wq)*sqrt(nk), fftisdf.py:205-207). */
+int isdf_ktransform_rows_ex(void* handle, const void* in, long in_sk, long in_sr, void* out, long out_sq, long out_sr,
+                            long out_c0, int nrows, int ncols, const int* kmesh, const void* uaxes_host, int conj2,
+                            const int* qslot, const int* rowmap, long rowmap_sq, double* diag, int mode,
+                            const double* table, long tab_sk, long tab_sr, double scale, void* stream);
+
+/* J/K consumers (fftisdf.py:133-228) building blocks:
+ * isdf_gemm_hn: c[z] = a[z]^H b[z], a [k][m], b [k][n] row-major (X_k^H (...) at :166, :225);
+ * isdf_rowdot_conj_sum: out[i] = scale * sum_z sum_n y[z][i][n] conj(x[z][i][n])  (rho_I, :155-156);
+ * isdf_scale_rows: out[z][i][n] = v[i] * x[z][i][n]  (diag(v) X_k, :166). */
+int isdf_gemm_hn(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB, void* c,
+                 long ldc, long strideC, int m, int n, int k, int batch, void* stream);
+int isdf_rowdot_conj_sum(void* handle, const void* y, const void* x, int nz, int nrows, int ncols, double scale,
+                         void* out, void* stream);
+int isdf_scale_rows(void* handle, const void* x, const void* v, int nz, int nrows, int ncols, void* out, void* stream);
+
 /* fftisdf.py:108  scipy.linalg.lstsq(A_q, Y_q^T): block operators of the two triangular sweeps from the
  * pivoted factor (block size 64).  n = nip, nP = multiple of 64 >= max(rank) (usually n rounded up).  lfwd, ubwd [batch][nP][nP];
  * work 2*batch*nP*nP c128.  Rows/columns at positions >= rank are replaced by the identity. */

@@ -149,3 +149,51 @@ def test_reference_error_conventions():
     with pytest.raises(NotImplementedError):
         df.get_jk(dm, exxdiv="ewald")                 # fftisdf.py:395-396
     assert df._x.shape[0] == 2 and df._wq.shape[0] == 2 and df._w0.shape == df._wq.shape[1:]
+
+
+def test_eri_reconstruction_against_exact_pair_densities():
+    """the reference's de-facto acceptance test (fftdf-with-k-lstsq.py:219-258, abort above 1e-4):
+    einsum("IJ,Im,In,Jk,Jl->mnkl", W_q, x1*, x2, x3*, x4) against the exact ERI of the same pair densities
+    evaluated on the dense grid with the same Coulomb kernel (PySCF-free stand-in for FFTDF.get_eri)."""
+    import fft_isdf_scratch_b200 as pk
+    from fft_isdf_scratch_b200 import fftisdf
+    cell = pk.random_cubic_cell(14, 6, seed=41, L=7.0, ltypes="sp")
+    kmesh = [2, 1, 1]
+    kpts = cell.get_kpts(kmesh)
+    df = fftisdf.ISDF(cell, kpts, m0=[9, 9, 9], c0=12.0)
+    df.ao_on_device = False
+    df.build()
+    x, wq = df._x, df._wq
+    coord = cell.gen_uniform_grids(cell.mesh)
+    phi = cell.eval_ao_kpts(coord, df.kpts)              # [nk, ng, nao]
+    ng = len(coord)
+    mesh = cell.mesh
+    worst = 0.0
+    for k1 in range(2):
+        for k2 in range(2):
+            q = (k2 - k1) % 2                              # pair momentum k2 - k1
+            for k3 in range(2):
+                k4 = (k3 - q) % 2
+                fq = np.exp(-1j * coord @ df.kpts[q])
+                cg = H.get_coulG(cell.a, df.kpts[q], mesh)
+                rho12 = np.einsum("gm,gn->mng", phi[k1].conj(), phi[k2]).reshape(-1, ng)
+                rho34 = np.einsum("gk,gl->klg", phi[k3].conj(), phi[k4]).reshape(-1, ng)
+                zeta = H.ifft(H.fft(rho12 * fq, mesh) * cg * cell.vol / ng, mesh) * fq.conj()
+                eri_ref = zeta @ rho34.T
+                eri = O.eri_from_w(wq[q], x[k1], x[k2], x[k3], x[k4]).reshape(eri_ref.shape)
+                worst = max(worst, float(np.abs(eri - eri_ref).max() / np.abs(eri_ref).max()))
+    assert worst < 1e-4, worst
+
+
+@pytest.mark.parametrize("name", ["k321_spd", "k231_odd", "gamma_s"])
+def test_device_jk_equals_host_jk_and_reference(name):
+    """get_j_kpts / get_k_kpts on the device == the numpy statement of fftisdf.py:133-228 == golden."""
+    g, df = run_golden(name)
+    dm2 = np.stack([g["dm"], g["dm"].conj().transpose(0, 2, 1) * 0.5])      # two density-matrix sets
+    df.jk_on_device = True
+    vj_d, vk_d = df.get_jk(dm2, kpts=g["kpts"])
+    df.jk_on_device = False
+    vj_h, vk_h = df.get_jk(dm2, kpts=g["kpts"])
+    assert rel(vj_d, vj_h) < 1e-12 and rel(vk_d, vk_h) < 1e-12
+    assert rel(vj_d[0], g["vj"].reshape(vj_d[0].shape)) < 1e-10
+    assert rel(vk_d[0], g["vk"].reshape(vk_d[0].shape)) < 1e-10

@@ -150,7 +150,12 @@ pchol_panel_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n,
       for (int c = 0; c < 4; ++c) {
         const int i = tid + (c0 + c) * PC_THREADS;
         act[c] = (i < n) && (i != p) && (mypos[c0 + c] > j);
-        v[c] = act[c] ? Arow[i] : make_double2(0.0, 0.0);
+        // row p of the Hermitian matrix from its LOWER triangle: A[p][i] (i < p) or conj(A[i][p]) (i > p)
+        v[c] = make_double2(0.0, 0.0);
+        if (act[c]) {
+          if (i < p) v[c] = Arow[i];
+          else { const cplx w = A[(long)i * lda + p]; v[c] = make_double2(w.x, -w.y); }
+        }
       }
       for (int tt = 0; tt < t; ++tt) {
         const cplx bb = bp[tt];
@@ -337,7 +342,11 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
       const int lc = tid + c * PCC_THREADS;
       const int i = c_lo + lc;
       act[c] = (lc < ncc) && (i < n) && (i != p) && (mypos[c] > j);
-      v[c] = act[c] ? Arow[i] : make_double2(0.0, 0.0);
+      v[c] = make_double2(0.0, 0.0);
+      if (act[c]) {   // row p from the lower triangle
+        if (i < p) v[c] = Arow[i];
+        else { const cplx w = A[(long)i * lda + p]; v[c] = make_double2(w.x, -w.y); }
+      }
     }
     for (int tt = 0; tt < t; ++tt) {
       const cplx bb = bp[tt];
@@ -530,7 +539,8 @@ extern "C" int isdf_pchol_workspace_bytes(int n, int batch, size_t* bytes) {
   return ISDF_OK;
 }
 
-// a: [batch][n][n] c128 Hermitian PSD, overwritten by its trailing Schur complements.
+// a: [batch][n][n] c128 Hermitian PSD (only the LOWER triangle is read), lower triangle overwritten by the
+// trailing Schur complements.
 // u: [batch][ldu_rows][n] c128, rows j < rank hold row j of the factor A = U^H U in ORIGINAL column
 //    order (column piv[j] carries the pivot); must be zero-initialised by the caller? -> zeroed here.
 extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
@@ -590,7 +600,7 @@ extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, do
       p.M = n; p.N = n; p.K = nb;
       p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
       p.perm = nullptr; p.stridePerm = 0; p.active = active;
-      ISDF_CUDA(h, (launch_gemm<128, 64, true, true, MODE_CONJA, false, EPI_SUB_HERM>(p, batch, st)));
+      ISDF_CUDA(h, (launch_gemm<128, 64, true, true, MODE_CONJA, false, EPI_SUB_LOWER>(p, batch, st)));
     }
   }
   {

@@ -35,7 +35,7 @@ int isdf_select_gram(void* handle, const void* x0, int nk, int n0, int nao, void
 
 /* fftisdf.py:381-382  pyscf.lib.scipy_helper.pivoted_cholesky -> LAPACK dpstrf (upper), and the
  * rank-revealing factorisation used in place of the QRCP inside scipy lstsq(..., "gelsy") at :108.
- * a [batch][n][n] Hermitian PSD (destroyed).  Runs at most max_steps pivots, stops earlier when the
+ * a [batch][n][n] Hermitian PSD, lower triangle referenced (destroyed).  Runs at most max_steps pivots, stops earlier when the
  * pivot <= tol (tol < 0: n*eps*max diag, LAPACK's default).  nb = panel width (<= 64, 0 -> 32).
  * u [batch][ldu_rows][n]: row j = row j of U (A = U^H U) in ORIGINAL column order.
  * piv [batch][n] (0-based, position -> original index), rank [batch], next_pivot [batch] (value of the

@@ -13,6 +13,7 @@ struct Handle {
   int device;
   int sm_count;
   int max_smem_optin;
+  void* scratch; size_t scratch_bytes;   // grow-only device scratch owned by the handle (split-K partials)
   char err[512];
 };
 

@@ -29,6 +29,7 @@ struct GemmParams {
   double alpha;
   const int* perm; long stridePerm;  // EPI_HERK: optional row/col scatter map per batch
   const int* active;                 // optional per-batch flag; batch skipped when 0
+  int ksplit; int kchunk; long strideSplit;  // split-K: grid.z = batch*ksplit, partial results at C + ks*strideSplit
 };
 
 #ifndef ISDF_GEMM_BK
@@ -68,7 +69,9 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
   cplx* sA = reinterpret_cast<cplx*>(smem_raw);
   cplx* sB = sA + STAGES * A_TILE;
 
-  const int bz = blockIdx.z;
+  int bz = blockIdx.z;
+  int ksp = 0;
+  if (p.ksplit > 1) { ksp = bz % p.ksplit; bz /= p.ksplit; }
   if (p.active != nullptr && p.active[bz] == 0) return;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (SYMM && n0 >= m0 + BM) return;  // tile strictly above the diagonal: produced by mirroring
@@ -76,9 +79,17 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp / WARPS_N) * 32, wn0 = (warp % WARPS_N) * 16;
-  const int M = p.M, N = p.N, K = p.K;
+  const int M = p.M, N = p.N;
+  int K = p.K;
   const cplx* Abase = p.A + (long)bz * p.strideA;
   const cplx* Bbase = p.B + (long)bz * p.strideB;
+  if (p.ksplit > 1) {   // this CTA contracts over k in [k0, k0 + kchunk)
+    const int k0 = ksp * p.kchunk;
+    Abase += A_KSLOW ? (long)k0 * p.lda : (long)k0;
+    Bbase += B_KSLOW ? (long)k0 * p.ldb : (long)k0;
+    K = (K - k0 < p.kchunk) ? (K - k0) : p.kchunk;
+    if (K < 0) K = 0;
+  }
   const int ktiles = (K + BK - 1) / BK;
   const int nit = p.nseg * ktiles;
 
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
   }
   cp_async_wait<0>();
 
-  cplx* Cb = p.C + (long)bz * p.strideC;
+  cplx* Cb = p.C + (long)bz * p.strideC + (long)ksp * p.strideSplit;
   const int* perm = (EPI == EPI_HERK && p.perm != nullptr) ? p.perm + (long)bz * p.stridePerm : nullptr;
   const double alpha = p.alpha;
 #pragma unroll
@@ -253,7 +264,7 @@ inline cudaError_t launch_gemm(const GemmParams& p, int batch, cudaStream_t st) 
     configured = true;
   }
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch * (p.ksplit > 1 ? p.ksplit : 1));
   kern<<<grid, gemm_threads(BM, BN), S::BYTES, st>>>(p);
   return cudaGetLastError();
 }

@@ -23,6 +23,26 @@ __global__ void gather_rows_kernel(const cplx* __restrict__ src, long lds, long 
     d[c] = (r >= 0) ? s[c] : make_double2(0.0, 0.0);
 }
 
+// W[z][perm[r]][perm[c]] = alpha * sum_ks part[ks][z][r][c] for r >= c, mirrored (deterministic split-K reduce)
+__global__ void herk_splitk_reduce_kernel(const cplx* __restrict__ part, int ksplit, long strideSplit, int n,
+                                          double alpha, const int* __restrict__ perm, long stridePerm,
+                                          cplx* __restrict__ w, long ldw, long strideW) {
+  const int z = blockIdx.z;
+  const int r = blockIdx.y * 16 + threadIdx.y;
+  const int c = blockIdx.x * 16 + threadIdx.x;
+  if (r >= n || c > r) return;
+  double sr = 0.0, si = 0.0;
+  for (int ks = 0; ks < ksplit; ++ks) {
+    const cplx v = part[(long)ks * strideSplit + ((long)z * n + r) * n + c];
+    sr += v.x; si += v.y;
+  }
+  const int* pm = perm ? perm + (long)z * stridePerm : nullptr;
+  const int pr = pm ? pm[r] : r, pc = pm ? pm[c] : c;
+  cplx* W = w + (long)z * strideW;
+  W[(long)pr * ldw + pc] = make_double2(alpha * sr, (r == c) ? 0.0 : alpha * si);
+  if (r > c) W[(long)pc * ldw + pr] = make_double2(alpha * sr, -alpha * si);
+}
+
 // out[i] = scale * sum_z sum_n y[z][i][n] * conj(x[z][i][n])          (fftisdf.py:155-156, rho_I)
 __global__ void rowdot_conj_sum_kernel(const cplx* __restrict__ y, const cplx* __restrict__ x, int nz, int nrows,
                                        int ncols, double scale, cplx* __restrict__ out) {
@@ -79,6 +99,7 @@ extern "C" int isdf_create(int device, void** out) {
     delete h;
     return ISDF_ESIZE;
   }
+  h->scratch = nullptr; h->scratch_bytes = 0;
   h->sm_count = prop.multiProcessorCount;
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   *out = h;
@@ -92,6 +113,7 @@ extern "C" int isdf_destroy(void* hv) {
   if (!hv) return ISDF_OK;
   isdf_fft_release_plans(hv);
   dft_release_plans_internal(((Handle*)hv)->device);
+  if (((Handle*)hv)->scratch) cudaFree(((Handle*)hv)->scratch);
   delete (Handle*)hv;
   return ISDF_OK;
 }
@@ -112,7 +134,7 @@ extern "C" int isdf_select_gram(void* hv, const void* x0, int nk, int n0, int na
   p.M = n0; p.N = n0; p.K = nao;
   p.nseg = nk; p.segA = (long)n0 * nao; p.segB = (long)n0 * nao;
   p.alpha = 1.0 / (double)nk;
-  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
   ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJA, true, EPI_SQ_SYM>(p, 1, (cudaStream_t)stream)));
   return ISDF_OK;
 }
@@ -130,7 +152,7 @@ extern "C" int isdf_gram_conja(void* hv, const void* a, long lda, long strideA, 
   p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
   p.M = m; p.N = n; p.K = k;
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
-  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
   ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJA, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
   return ISDF_OK;
 }
@@ -148,7 +170,7 @@ extern "C" int isdf_gram_conjb(void* hv, const void* a, long lda, long strideA, 
   p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
   p.M = m; p.N = n; p.K = k;
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
-  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
   ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
   return ISDF_OK;
 }
@@ -159,6 +181,7 @@ extern "C" int isdf_herk_scatter(void* hv, const void* b, long ldb, long strideB
                                  const int* perm, long stridePerm, void* w, long ldw, long strideW, int batch,
                                  void* stream) {
   Handle* h = (Handle*)hv;
+  cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, b && w, "null pointer");
   ISDF_CHECK_ARG(h, n >= 0 && k >= 0 && batch >= 0 && batch <= 65535, "shape");
   GemmParams p;
@@ -167,8 +190,37 @@ extern "C" int isdf_herk_scatter(void* hv, const void* b, long ldb, long strideB
   p.C = (cplx*)w; p.ldc = ldw; p.strideC = strideW;
   p.M = n; p.N = n; p.K = k;
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = alpha;
-  p.perm = perm; p.stridePerm = stridePerm; p.active = nullptr;
-  ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_HERK>(p, batch, (cudaStream_t)stream)));
+  p.perm = perm; p.stridePerm = stridePerm; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
+  // Small n, long K: the lower-tile grid alone does not fill the GPU (2 CTAs per SM), so the contraction is split
+  // along K into partial products that a second kernel sums in a fixed order (deterministic, exactly Hermitian).
+  const long nt = (n + 63) / 64;
+  const long tiles = nt * (nt + 1) / 2 * batch;
+  const long slots = 2L * h->sm_count;
+  int ksplit = 1;
+  if (tiles < 4 * slots && k >= 4096) {
+    ksplit = (int)((4 * slots + tiles - 1) / tiles);
+    if (ksplit > 16) ksplit = 16;
+    while (ksplit > 1 && k / ksplit < 1024) --ksplit;
+  }
+  if (ksplit <= 1) {
+    ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_HERK>(p, batch, st)));
+    return ISDF_OK;
+  }
+  const size_t need = (size_t)ksplit * batch * n * n * sizeof(cplx);
+  if (h->scratch_bytes < need) {
+    if (h->scratch) ISDF_CUDA(h, cudaFree(h->scratch));
+    h->scratch = nullptr; h->scratch_bytes = 0;
+    ISDF_CUDA(h, cudaMalloc(&h->scratch, need));
+    h->scratch_bytes = need;
+  }
+  p.C = (cplx*)h->scratch; p.ldc = n; p.strideC = (long)n * n;
+  p.perm = nullptr; p.stridePerm = 0; p.alpha = 1.0;
+  p.ksplit = ksplit; p.kchunk = ((k + ksplit - 1) / ksplit + 15) / 16 * 16; p.strideSplit = (long)batch * n * n;
+  ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_HERK>(p, batch, st)));
+  dim3 grid((n + 15) / 16, (n + 15) / 16, batch), block(16, 16);
+  herk_splitk_reduce_kernel<<<grid, block, 0, st>>>((const cplx*)h->scratch, ksplit, p.strideSplit, n, alpha, perm,
+                                                    stridePerm, (cplx*)w, ldw, strideW);
+  ISDF_LAUNCH_CHECK(h);
   return ISDF_OK;
 }
 
@@ -184,7 +236,7 @@ extern "C" int isdf_gemm_nn(void* hv, const void* a, long lda, long strideA, con
   p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
   p.M = m; p.N = n; p.K = k;
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
-  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
   ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
   return ISDF_OK;
 }
@@ -201,7 +253,7 @@ extern "C" int isdf_gemm_hn(void* hv, const void* a, long lda, long strideA, con
   p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
   p.M = m; p.N = n; p.K = k;
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
-  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
   ISDF_CUDA(h, (launch_gemm<128, 64, true, true, MODE_CONJA, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
   return ISDF_OK;
 }

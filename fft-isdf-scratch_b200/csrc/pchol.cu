@@ -599,7 +599,7 @@ extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, do
       p.C = (cplx*)a; p.ldc = n; p.strideC = strideA;
       p.M = n; p.N = n; p.K = nb;
       p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
-      p.perm = nullptr; p.stridePerm = 0; p.active = active;
+      p.perm = nullptr; p.stridePerm = 0; p.active = active; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
       ISDF_CUDA(h, (launch_gemm<128, 64, true, true, MODE_CONJA, false, EPI_SUB_LOWER>(p, batch, st)));
     }
   }
@@ -660,7 +660,7 @@ extern "C" int isdf_trsm_sweeps(void* hv, const void* lfwd, const void* ubwd, vo
   p.ldc = ldt; p.strideC = (long)nP * ldt;
   p.M = TB; p.N = (int)ng;
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
-  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
   for (int a = 0; a < nblk; ++a) {  // forward: rows 0..a
     p.A = (const cplx*)lfwd + (long)a * TB * nP;
     p.B = (const cplx*)t;

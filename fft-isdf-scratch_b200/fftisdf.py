@@ -138,6 +138,28 @@ def build(df_obj):
         ev[name] = e
 
     mark("start")
+    # Host AO table of the dense grid: start its (pinned, per-k) upload on a side stream now, so that it
+    # overlaps the selection and metric stages; the right-hand-side stage waits on the event.
+    grids = df_obj.grids
+    coord = numpy.asarray(grids.coords)
+    ngrid = coord.shape[0]
+    g_lo, g_hi, ncol = sharding.col_shard(ngrid, world, rank)
+    tab = getattr(df_obj, "_ao_tables", None)
+    upload_done = None
+    if tab is not None and not torch.is_tensor(tab) and tab[:, g_lo:g_hi].nbytes <= df_obj.table_upload_limit:
+        stats["h2d_bytes"] += tab[:, g_lo:g_hi].nbytes
+        side = df_obj.__dict__.setdefault("_side_stream", torch.cuda.Stream(device=dev))
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            tab_dev = _rows_to_dev(ops, tab, g_lo, g_hi)
+            upload_done = torch.cuda.Event()
+            upload_done.record(side)
+        tab_dev.record_stream(torch.cuda.current_stream())
+        df_obj._ao_tables_dev = (tab_dev, g_lo)
+    elif torch.is_tensor(tab):
+        df_obj._ao_tables_dev = (tab, 0)
+    else:
+        df_obj._ao_tables_dev = None
     # ---- A. interpolation points                                              :33 -> :357-388
     xip = df_obj.select_interpolation_points(_device_result=True)
     nip = xip.shape[1]
@@ -211,10 +233,6 @@ def build(df_obj):
     mark("metric")
 
     # ---- B2. right-hand side Y_q^T for this rank's grid columns, written straight into pivot order  :72-87
-    grids = df_obj.grids
-    coord = numpy.asarray(grids.coords)
-    ngrid = coord.shape[0]
-    g_lo, g_hi, ncol = sharding.col_shard(ngrid, world, rank)
     _log(df_obj, "nkpt = %d, ngrid = %d, nip = %d", nkpt, ngrid, nip)
     # Y^T, then Theta, then B (in place).  Multi-GPU with a tensor-core-DFT mesh: the buffer lives in NVLink
     # peer-mapped memory so that the FFT kernels gather/scatter it directly (no all-to-all, no permute copies).
@@ -232,15 +250,8 @@ def build(df_obj):
         theta = torch.zeros((nq, nipP, ncol), dtype=torch.complex128, device=dev)
     blksize = int(df_obj.blksize)
     fx_k = None
-    tab = getattr(df_obj, "_ao_tables", None)
-    if tab is not None and not torch.is_tensor(tab) and tab[:, g_lo:g_hi].nbytes <= df_obj.table_upload_limit:
-        # host AO table that fits: one pinned H2D copy of this rank's rows, blocks are then device views
-        stats["h2d_bytes"] += tab[:, g_lo:g_hi].nbytes
-        df_obj._ao_tables_dev = (_rows_to_dev(ops, tab, g_lo, g_hi), g_lo)
-    elif torch.is_tensor(tab):
-        df_obj._ao_tables_dev = (tab, 0)
-    else:
-        df_obj._ao_tables_dev = None
+    if upload_done is not None:
+        torch.cuda.current_stream().wait_event(upload_done)
     for ao_k_etc, g0, g1 in df_obj.aoR_loop(grids, vk, 0, blksize=blksize, g_range=(g_lo, g_hi)):   # :72
         f_k = ao_k_etc[0]
         if not torch.is_tensor(f_k):

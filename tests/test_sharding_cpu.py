@@ -45,7 +45,7 @@ WORKER = textwrap.dedent('''
     S.broadcast_(t, 0, dist.group.WORLD)
     assert torch.equal(t.real, torch.ones(3, dtype=torch.float64))
     dist.destroy_process_group()
-    print("rank", r, "ok")
+    open(sys.argv[1] + f"/ok{r}", "w").write("ok")
 ''')
 
 
@@ -54,10 +54,10 @@ def test_layouts_world2_gloo(tmp_path):
     script.write_text(WORKER % ROOT)
     env = dict(os.environ, OMP_NUM_THREADS="1")
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), str(tmp_path)],
                        capture_output=True, text=True, env=env, timeout=240)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
-    assert "rank 0 ok" in p.stdout and "rank 1 ok" in p.stdout
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
 def test_col_shard_covers_grid():

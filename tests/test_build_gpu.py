@@ -197,3 +197,58 @@ def test_device_jk_equals_host_jk_and_reference(name):
     assert rel(vj_d, vj_h) < 1e-12 and rel(vk_d, vk_h) < 1e-12
     assert rel(vj_d[0], g["vj"].reshape(vj_d[0].shape)) < 1e-10
     assert rel(vk_d[0], g["vk"].reshape(vk_d[0].shape)) < 1e-10
+
+
+def _run_synth(cell, kmesh, m0, c0, **attrs):
+    from fft_isdf_scratch_b200 import fftisdf
+    kpts = cell.get_kpts(kmesh)
+    df = fftisdf.ISDF(cell, kpts, m0=m0, c0=c0)
+    df.ao_on_device = False
+    for k, v in attrs.items():
+        setattr(df, k, v)
+    df.build()
+    x0 = cell.eval_ao_kpts(cell.gen_uniform_grids(m0), df.kpts)
+    coord = cell.gen_uniform_grids(cell.mesh)
+    f_all = cell.eval_ao_kpts(coord, df.kpts)
+    out = O.build(cell.a, df.kpts, kmesh, cell.mesh, x0, f_all, coord, c0)
+    return df, out
+
+
+def test_fallback_kernels_large_kmesh_axis_and_long_fft_axis():
+    """k-mesh axis 5 (shared-memory k-transform, numpy J/K statement) and a 50-point FFT axis (Stockham kernel
+    instead of the tensor-core DFT) through the same build(): same parity bar as the fast paths."""
+    import fft_isdf_scratch_b200 as pk
+    cell = pk.random_cubic_cell(12, 10, seed=52, L=8.0, ltypes="spd")
+    cell.mesh = [50, 8, 9]                      # cond(A_q) ~ 3e2 at c0 = 2: strict parity applies
+    df, out = _run_synth(cell, [5, 1, 1], [7, 7, 7], 2.0, blksize=1000)
+    assert np.array_equal(df._mask, out["mask"]) and np.array_equal(df._x, out["x"])
+    conds = [np.linalg.cond(m) for m in out["x4_k"]]
+    tol = max(1e-10, 50 * max(conds) * 2.2e-16)
+    assert rel(df._wq, out["wq"]) < tol, (rel(df._wq, out["wq"]), max(conds))
+    nk, nao = len(df.kpts), cell.nao_nr()
+    rng = np.random.default_rng(5)
+    dm = rng.standard_normal((nk, nao, nao)) + 1j * rng.standard_normal((nk, nao, nao))
+    dm = dm + dm.conj().transpose(0, 2, 1)
+    import fft_isdf_scratch_b200 as pk2
+    tr = pk2.pbc_tools.time_reversal_partner([5, 1, 1])
+    dm = 0.5 * (dm + dm[tr].conj())
+    vj, vk = df.get_jk(dm, kpts=df.kpts)
+    ph = H.get_phase(cell.a, df.kpts, [5, 1, 1])
+    vj_ref = O.get_j_kpts(out["x"], out["wq"][0], dm[None])[0]
+    vk_ref = O.get_k_kpts(out["x"], out["wq"], dm[None], ph)[0]
+    assert rel(vj, vj_ref) < tol and rel(vk, vk_ref) < tol
+
+
+def test_all_parent_points_selected_and_single_block():
+    """Edge sizes: c0 so large that nip is limited by the pivoted-Cholesky rank / the parent grid (fftisdf.py:383),
+    one aoR block covering the whole grid, Gamma point only."""
+    import fft_isdf_scratch_b200 as pk
+    cell = pk.random_cubic_cell(10, 3, seed=61, L=6.0, ltypes="s")
+    df, out = _run_synth(cell, [1, 1, 1], [3, 3, 3], 50.0, blksize=100000)
+    assert df._x.shape[1] == out["x"].shape[1] <= 27
+    assert np.array_equal(df._mask, out["mask"])
+    # nip is rank-limited here (A_q at the edge of numerical rank): check structure, not digits
+    w = df._wq[0]
+    assert np.isfinite(w).all() and np.abs(w - w.conj().T).max() == 0.0
+    vj, vk = df.get_jk(np.eye(3)[None] + 0j, kpts=df.kpts)
+    assert np.isfinite(vj).all() and np.isfinite(vk).all()

@@ -260,15 +260,21 @@ def build(df_obj):
             stats["h2d_bytes"] += f_k.nbytes
             f_k = _to_dev(ops, f_k)
         blk = g1 - g0
-        if fx_k is None or fx_k.numel() != nkpt * blk * nip:
-            fx_k = torch.empty((nkpt * blk * nip,), dtype=torch.complex128, device=dev)
         if reg_path:
             # transposed product fx^T[k][I][g] = X_k F_k^H (:76), so the elementwise stage streams along g
-            fxt = fx_k.view(nkpt, nip, blk)
-            ops.gram_conjb(xip, f_k, out=fxt)
-            ops.ktransform_rows(fxt, nip * blk, blk, theta, nipP * ncol, ncol, g0 - g_lo, nip, blk, kmesh, uax_h,
-                                conj2=0, qslot=qslot, rowmap=rowmap, rowmap_sq=nip, diag=diag[2:4])   # :79-85
+            # (optionally in L2-sized sub-blocks, see rhs_l2_bytes)
+            sub = max(64, min(blk, int(df_obj.rhs_l2_bytes // (nkpt * nip * 16)) // 64 * 64))
+            if fx_k is None or fx_k.numel() != nkpt * sub * nip:
+                fx_k = torch.empty((nkpt * sub * nip,), dtype=torch.complex128, device=dev)
+            for s0 in range(0, blk, sub):
+                sb = min(sub, blk - s0)
+                fxt = fx_k[: nkpt * nip * sb].view(nkpt, nip, sb)
+                ops.gram_conjb(xip, f_k[:, s0:s0 + sb, :], out=fxt)
+                ops.ktransform_rows(fxt, nip * sb, sb, theta, nipP * ncol, ncol, g0 - g_lo + s0, nip, sb, kmesh, uax_h,
+                                    conj2=0, qslot=qslot, rowmap=rowmap, rowmap_sq=nip, diag=diag[2:4])   # :79-85
         else:
+            if fx_k is None or fx_k.numel() != nkpt * blk * nip:
+                fx_k = torch.empty((nkpt * blk * nip,), dtype=torch.complex128, device=dev)
             fx = fx_k.view(nkpt, blk, nip)
             ops.gram_conja(f_k, xip, out=fx)                                  # :76
             ops.ktransform_square(fx, blk * nip, nip, theta, nipP * ncol, 1, ncol, g0 - g_lo, blk, nip, kmesh, uax,
@@ -500,6 +506,10 @@ class InterpolativeSeparableDensityFitting(_Base):
     blksize = 8000   # block size for the aoR_loop            (fftisdf.py:300)
     chol_nb = 32     # panel width of the pivoted Cholesky kernels
     table_upload_limit = 48 * 2 ** 30  # host AO tables up to this size are uploaded in one copy
+    # Optional cut of each aoR block into sub-blocks whose fx^T stays L2-resident between the GEMM and the
+    # k-transform.  Measured SLOWER on B200 (rhs 17 ms unblocked vs 21-37 ms at 96-16 MB: the stage is launch/
+    # latency bound, not HBM bound), so it is off by default.
+    rhs_l2_bytes = 1 << 62
 
     def __init__(self, cell, kpts, m0=None, c0=20.0, device=0):
         super().__init__(cell, kpts)

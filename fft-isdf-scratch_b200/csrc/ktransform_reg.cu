@@ -48,6 +48,31 @@ __device__ __forceinline__ void dft_axis(cplx (&x)[NK]) {
   }
 }
 
+// First pass of the second transform: the input is real (y_s = s*s), half the FMAs.
+template <int N, int STRIDE, int NK, int AX, bool CONJ>
+__device__ __forceinline__ void dft_axis_real_in(cplx (&x)[NK]) {
+  if constexpr (N > 1) {
+#pragma unroll
+  for (int base = 0; base < NK; ++base) {
+    if ((base / STRIDE) % N != 0) continue;
+    double t[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) t[j] = x[base + j * STRIDE].x;
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const cplx u = c_uax[AX][m][j];
+        re = fma(u.x, t[j], re);
+        im = fma(CONJ ? -u.y : u.y, t[j], im);
+      }
+      x[base + m * STRIDE] = make_double2(re, im);
+    }
+  }
+  }
+}
+
 template <int N1, int N2, int N3>
 __global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
   constexpr int NK = N1 * N2 * N3;
@@ -70,15 +95,17 @@ __global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
       else if (p.mode == 1) x[k] = make_double2(p.scale * x[k].x * p.table[(long)k * p.tab_sk + (long)r * p.tab_sr + c], 0.0);
       else reinterpret_cast<double*>(p.out)[(long)k * p.out_sq + (long)r * p.out_sr + p.out_c0 + c] = p.scale * x[k].x;
     }
+    // second transform: its first non-trivial pass sees real input (y_s is real) -> half the FMAs there
+    constexpr bool R3 = N3 > 1, R2 = !R3 && N2 > 1, R1 = !R3 && !R2;
     if (p.mode == 2) {
     } else if (p.conj2) {
-      dft_axis<N3, 1, NK, 2, true>(x);
-      dft_axis<N2, N3, NK, 1, true>(x);
-      dft_axis<N1, N2 * N3, NK, 0, true>(x);
+      if (R3) dft_axis_real_in<N3, 1, NK, 2, true>(x); else dft_axis<N3, 1, NK, 2, true>(x);
+      if (R2) dft_axis_real_in<N2, N3, NK, 1, true>(x); else dft_axis<N2, N3, NK, 1, true>(x);
+      if (R1) dft_axis_real_in<N1, N2 * N3, NK, 0, true>(x); else dft_axis<N1, N2 * N3, NK, 0, true>(x);
     } else {
-      dft_axis<N3, 1, NK, 2, false>(x);
-      dft_axis<N2, N3, NK, 1, false>(x);
-      dft_axis<N1, N2 * N3, NK, 0, false>(x);
+      if (R3) dft_axis_real_in<N3, 1, NK, 2, false>(x); else dft_axis<N3, 1, NK, 2, false>(x);
+      if (R2) dft_axis_real_in<N2, N3, NK, 1, false>(x); else dft_axis<N2, N3, NK, 1, false>(x);
+      if (R1) dft_axis_real_in<N1, N2 * N3, NK, 0, false>(x); else dft_axis<N1, N2 * N3, NK, 0, false>(x);
     }
 #pragma unroll
     for (int q = 0; q < NK; ++q) {

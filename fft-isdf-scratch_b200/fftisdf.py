@@ -222,8 +222,9 @@ def build(df_obj):
         lf_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
         ub_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
     del u_q
-    lfwd = sharding.allgather_slots(lf_l, nq, comm)
-    ubwd = sharding.allgather_slots(ub_l, nq, comm)
+    # the (large) all-gather of the sweep operators runs on NCCL's stream while the right-hand side is built
+    lfwd_g = sharding.AsyncSlotGather(lf_l, nq, comm)
+    ubwd_g = sharding.AsyncSlotGather(ub_l, nq, comm)
     del lf_l, ub_l
     rowmap_h = -numpy.ones((nq, nip), dtype=numpy.int32)
     for s in range(nq):
@@ -286,6 +287,8 @@ def build(df_obj):
     mark("rhs")
 
     # ---- C(b). Theta_q = A_q^+ Y_q^T by two blocked triangular sweeps, all q at once  :108
+    lfwd, ubwd = lfwd_g.result(), ubwd_g.result()
+    del lfwd_g, ubwd_g
     ops.trsm_sweeps(lfwd, ubwd, theta)
     del lfwd, ubwd
     mark("fit")
@@ -319,6 +322,8 @@ def build(df_obj):
         if world > 1:
             del theta
         nv, ldv = vecs.shape[1], vecs.shape[2]
+        if world == 1:
+            nv = min(nv, int(rank_h.max()))      # rows at positions >= max rank are identically zero
         for s, q in enumerate(qind):                                              # :97
             ops.phase_table(coord_d, vk[q], fq_d)                                 # :99   fq = exp(-i r.q)
             ops.coulomb_weights(bvec, kscaled[q], mesh, vol, wgt_d)               # :114-115 sqrt(coulG vol)/ng

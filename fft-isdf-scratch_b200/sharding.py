@@ -97,6 +97,40 @@ def allgather_slots(local, nslot, group=None):
     return full
 
 
+class AsyncSlotGather:
+    """`allgather_slots` split in two so that the (large) gather of the sweep operators overlaps the right-hand
+    side stage: start() issues the NCCL all-gather asynchronously, result() waits and reorders the slots."""
+
+    def __init__(self, local, nslot, group=None):
+        self.local, self.nslot, self.group = local, nslot, group
+        self.world, self.rank = world_info(group)
+        self.work = None
+        if self.world == 1:
+            return
+        per = -(-nslot // self.world)
+        pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        self.flat = (torch.view_as_real(pad) if pad.is_complex() else pad).contiguous()
+        self.out = torch.empty((self.world * self.flat.shape[0],) + tuple(self.flat.shape[1:]), dtype=self.flat.dtype,
+                               device=self.flat.device)
+        self.work = dist.all_gather_into_tensor(self.out, self.flat, group=group, async_op=True)
+
+    def result(self):
+        if self.world == 1:
+            return self.local
+        self.work.wait()
+        out = self.out.reshape((self.world,) + tuple(self.flat.shape))
+        if self.local.is_complex():
+            out = torch.view_as_complex(out)
+        full = torch.empty((self.nslot,) + tuple(self.local.shape[1:]), dtype=self.local.dtype,
+                           device=self.local.device)
+        for r in range(self.world):
+            idx = slot_shard(self.nslot, self.world, r)
+            if idx:
+                full[idx] = out[r, : len(idx)]
+        return full
+
+
 def broadcast_(t, src=0, group=None):
     world, _ = world_info(group)
     if world > 1:

@@ -1,0 +1,33 @@
+"""bench.py contract checks that need no GPU: the reference arm (CPU oracle port) prints exactly one JSON line
+with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_flop_model_matches_oracle_model():
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import isdf_oracle as O
+    a = bench.flop_model(27, 26, 3375, 520, 50653)
+    b = O.flop_model(27, 26, 3375, 520, 50653)
+    assert a == b and 9.0e12 < a["total"] < 1.0e13      # cfg2 ~ 9.5e12

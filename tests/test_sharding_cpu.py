@@ -36,6 +36,8 @@ WORKER = textwrap.dedent('''
     lc = torch.stack([torch.full((2, 2), complex(s, -s), dtype=torch.complex128) for s in mine]) if mine else torch.zeros(0, 2, 2, dtype=torch.complex128)
     allc = S.allgather_slots(lc, nslot, dist.group.WORLD)
     assert torch.equal(allc[:, 0, 0].real, torch.arange(nslot, dtype=torch.float64))
+    agc = S.AsyncSlotGather(lc, nslot, dist.group.WORLD).result()
+    assert torch.equal(agc, allc)
     # partial W all-reduce == full contraction
     part = cols[:, :, : hi - lo] @ cols[:, :, : hi - lo].conj().transpose(1, 2)
     S.allreduce_sum_(part, dist.group.WORLD)

@@ -57,7 +57,9 @@ __device__ __forceinline__ void tile_mma(double (&re)[2], double (&im)[2], const
   }
 }
 
-template <bool GATHER>
+// PIPE (local data, n2 == n3): the DFT matrix is shared by both passes and the next plane is prefetched with
+// cp.async into a landing buffer while the current plane is transformed.
+template <bool GATHER, bool PIPE>
 __global__ void __launch_bounds__(DFT_THREADS, 2) dft_zy_kernel(DftParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n2 = p.n2, n3 = p.n3;
@@ -66,33 +68,59 @@ __global__ void __launch_bounds__(DFT_THREADS, 2) dft_zy_kernel(DftParams p) {
   cplx* Xs = reinterpret_cast<cplx*>(smem_raw);   // [n3p][LDX]   Xs[z][y]
   cplx* Ys = Xs + n3p * LDX;                      // [n3p][LDY]   Ys[kz][y]
   cplx* W3 = Ys + n3p * LDY;                      // [n3p][LDW3]  W3[z][kz]
-  cplx* W2 = W3 + n3p * LDW3;                     // [n2p][LDW2]  W2[y][ky]
+  cplx* W2 = PIPE ? W3 : W3 + n3p * LDW3;         // [n2p][LDW2]  W2[y][ky]  (same matrix when n2 == n3)
+  cplx* Ls = W3 + n3p * LDW3;                     // PIPE only: [n2*n3] raw landing buffer of the next plane
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int plane_sz = n2 * n3;
   fill_dft_matrix(W3, p.w3, n3p, LDW3);
-  fill_dft_matrix(W2, p.w2, n2p, LDW2);
+  if (!PIPE) fill_dft_matrix(W2, p.w2, n2p, LDW2);
+  auto prefetch = [&](long work) {
+    const int plane = (int)(work % p.n1);
+    const long vec = work / p.n1;
+    const cplx* src = p.data + vec * p.ldv + (long)plane * plane_sz;
+    for (int w = tid; w < plane_sz; w += DFT_THREADS) cp_async16(Ls + w, src + w, true);
+    cp_async_commit();
+  };
+  if (PIPE && (long)blockIdx.x < p.nwork) prefetch(blockIdx.x);
   // persistent over planes: the DFT matrices stay in shared memory
   for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
     const int plane = (int)(work % p.n1);
     const long vec = work / p.n1;
-    const long poff = (long)plane * n2 * n3;
+    const long poff = (long)plane * plane_sz;
     cplx* base = p.data + vec * p.ldv + poff;
-    // load plane transposed: Xs[z][y] = base[y*n3 + z] * pre ; zero padding
-    for (int w = tid; w < n3p * n2p; w += DFT_THREADS) {
-      const int y = w / n3p, z = w - y * n3p;   // z fastest: coalesced global reads
-      cplx v = make_double2(0.0, 0.0);
-      if (y < n2 && z < n3) {
-        if (GATHER) {
-          const long gidx = poff + y * n3 + z;
-          const int owner = (int)(gidx / p.ncol);
-          v = p.peer[owner][(p.row0 + vec) * p.ncol + (gidx - owner * p.ncol)];
-        } else {
-          v = base[y * n3 + z];
+    if (PIPE) {
+      cp_async_wait<0>();
+      __syncthreads();          // landing buffer complete; every warp is done with the previous plane
+      for (int w = tid; w < n3p * n2p; w += DFT_THREADS) {
+        const int y = w / n3p, z = w - y * n3p;
+        cplx v = make_double2(0.0, 0.0);
+        if (y < n2 && z < n3) {
+          v = Ls[y * n3 + z];
+          if (p.pre) v = cmul(v, p.pre[poff + y * n3 + z]);
         }
-        if (p.pre) v = cmul(v, p.pre[poff + y * n3 + z]);
+        Xs[z * LDX + y] = v;
       }
-      Xs[z * LDX + y] = v;
+      __syncthreads();
+      if (work + gridDim.x < p.nwork) prefetch(work + gridDim.x);   // flies during both passes
+    } else {
+      // load plane transposed: Xs[z][y] = base[y*n3 + z] * pre ; zero padding
+      for (int w = tid; w < n3p * n2p; w += DFT_THREADS) {
+        const int y = w / n3p, z = w - y * n3p;   // z fastest: coalesced global reads
+        cplx v = make_double2(0.0, 0.0);
+        if (y < n2 && z < n3) {
+          if (GATHER) {
+            const long gidx = poff + y * n3 + z;
+            const int owner = (int)(gidx / p.ncol);
+            v = p.peer[owner][(p.row0 + vec) * p.ncol + (gidx - owner * p.ncol)];
+          } else {
+            v = base[y * n3 + z];
+          }
+          if (p.pre) v = cmul(v, p.pre[poff + y * n3 + z]);
+        }
+        Xs[z * LDX + y] = v;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- pass 1: T[y][kz] = sum_z Xs[z][y] W3[z][kz]   -> Ys[kz][y]
     {
       const int mt_n = n2p >> 3, nt_n = n3p >> 3;
@@ -120,15 +148,15 @@ __global__ void __launch_bounds__(DFT_THREADS, 2) dft_zy_kernel(DftParams p) {
         }
       }
     }
-    // Xs is rewritten by the next plane's load only after every warp finished pass 1 (barrier above); Ys is
-    // rewritten in the next pass 1, which comes after the next load's barrier.
+    // non-PIPE: Xs is rewritten by the next plane's load only after every warp finished pass 1 (barrier
+    // above); Ys is rewritten in the next pass 1, which comes after the next load's barrier.
   }
 }
 
 constexpr int DFTX_LINES = 64;
 
 template <bool SCATTER>
-__global__ void __launch_bounds__(DFT_THREADS, 2) dft_x_kernel(DftParams p) {
+__global__ void __launch_bounds__(DFT_THREADS, SCATTER ? 2 : 3) dft_x_kernel(DftParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n1 = p.n1;
   const long n23 = (long)p.n2 * p.n3;
@@ -257,11 +285,17 @@ static int dft3d_run(Handle* h, cplx* local, long nvec, long ldv, const int* mes
   const size_t sm_x = (size_t)(n1p * (DFTX_LINES + 2) + n1p * (n1p + 2)) * sizeof(cplx);
   ISDF_CHECK_ARG(h, sm_zy <= (size_t)h->max_smem_optin && sm_x <= (size_t)h->max_smem_optin, "mesh too large");
   const bool p2p = peer != nullptr;
+  // in-place hazard of the pipelined variant: the prefetch of a later plane must not race with pass-2 stores of
+  // another CTA -- planes are disjoint, and a CTA only prefetches planes it will itself transform, so it is safe.
+  const size_t sm_pipe = (size_t)(n3p * (n2p + 2) + n3p * (n2p + 4) + n3p * (n3p + 2) + n2 * n3) * sizeof(cplx);
+  const bool pipe = !p2p && n2 == n3 && 2 * sm_pipe <= (size_t)h->max_smem_optin;
+  const size_t sm_zy_used = pipe ? sm_pipe : sm_zy;
   if (p2p) {
-    ISDF_CUDA(h, cudaFuncSetAttribute(dft_zy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_zy));
+    ISDF_CUDA(h, (cudaFuncSetAttribute(dft_zy_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_zy)));
     ISDF_CUDA(h, cudaFuncSetAttribute(dft_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
   } else {
-    ISDF_CUDA(h, cudaFuncSetAttribute(dft_zy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_zy));
+    if (pipe) ISDF_CUDA(h, (cudaFuncSetAttribute(dft_zy_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pipe)));
+    else ISDF_CUDA(h, (cudaFuncSetAttribute(dft_zy_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_zy)));
     ISDF_CUDA(h, cudaFuncSetAttribute(dft_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
   }
   // groups of vectors sized for L2 so that the x pass re-reads the zy pass's output from L2
@@ -275,8 +309,9 @@ static int dft3d_run(Handle* h, cplx* local, long nvec, long ldv, const int* mes
     p.row0 = row0 + v0;
     p.nwork = nv * n1;
     const unsigned g1 = (unsigned)((p.nwork < cap) ? p.nwork : cap);
-    if (p2p) dft_zy_kernel<true><<<g1, DFT_THREADS, sm_zy, st>>>(p);
-    else dft_zy_kernel<false><<<g1, DFT_THREADS, sm_zy, st>>>(p);
+    if (p2p) dft_zy_kernel<true, false><<<g1, DFT_THREADS, sm_zy, st>>>(p);
+    else if (pipe) dft_zy_kernel<false, true><<<g1, DFT_THREADS, sm_zy_used, st>>>(p);
+    else dft_zy_kernel<false, false><<<g1, DFT_THREADS, sm_zy, st>>>(p);
     ISDF_LAUNCH_CHECK(h);
     p.nwork = nv * ntile;
     const unsigned g2 = (unsigned)((p.nwork < cap) ? p.nwork : cap);

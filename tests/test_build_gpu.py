@@ -252,3 +252,40 @@ def test_all_parent_points_selected_and_single_block():
     assert np.isfinite(w).all() and np.abs(w - w.conj().T).max() == 0.0
     vj, vk = df.get_jk(np.eye(3)[None] + 0j, kpts=df.kpts)
     assert np.isfinite(vj).all() and np.isfinite(vk).all()
+
+
+def test_kmesh_metric_equals_supercell_pair_gram():
+    """BASELINE configs[2] / fftisdf-supercell-4.py:83-119: the k-mesh metric, unfolded with the Bloch phases, is the
+    Hadamard square of the pair Gram of the explicit k2gamma SUPERCELL (real-space, Gamma point) at the same points:
+    (P @ A_q)[R][I][J] == nk * ( sum_{S,mu} chi^sup_{S mu}(r_I) chi^sup_{S mu}(r_J + R) )^2."""
+    import fft_isdf_scratch_b200 as pk
+    from fft_isdf_scratch_b200 import fftisdf
+    T = pk.pbc_tools
+    cell = pk.random_cubic_cell(9, 5, seed=71, L=5.5, ltypes="sp")
+    kmesh = [3, 1, 2]
+    nk = 6
+    df = fftisdf.ISDF(cell, cell.get_kpts(kmesh), m0=[5, 5, 5], c0=2.0)
+    df.ao_on_device = False
+    df.keep_metric = True
+    df.use_time_reversal = False
+    df.build()
+    a_q = df._a_q.cpu().numpy()                                   # [nk, nip, nip]
+    phase = H.get_phase(cell.a, df.kpts, kmesh)
+    x4_s = (phase @ a_q.reshape(nk, -1)).reshape(a_q.shape)       # A = P^H x4_s  =>  x4_s = P A
+    assert np.abs(x4_s.imag).max() < 1e-12 * np.abs(x4_s).max()
+    # explicit supercell: lattice diag(kmesh) a, the primitive shells replicated on every image
+    rvec = T.translation_vectors_for_kmesh(cell.a, kmesh)
+    shells, i = [], 0
+    while i < cell.nao_nr():
+        l = {0: "s", 1: "p", 2: "d"}[sum(cell._terms[i][0][1])]
+        shells.append((cell._cen[i], l, cell._alp[i]))
+        i += {"s": 1, "p": 3, "d": 5}[l]
+    sup = pk.SyntheticCell(np.diag(kmesh) @ cell.a, [(c + r, l, al) for r in rvec for (c, l, al) in shells], [9, 9, 9])
+    pts = cell.gen_uniform_grids([5, 5, 5])[df._mask]
+    gam = np.zeros((1, 3))
+    phi0 = sup.eval_ao_kpts(pts, gam)[0].real
+    scale = nk * np.abs(phi0 @ phi0.T).max() ** 2          # the R = 0 block sets the scale; far blocks are tiny
+    for ir, r in enumerate(rvec):
+        gram = phi0 @ sup.eval_ao_kpts(pts + r, gam)[0].real.T
+        ref = nk * gram ** 2
+        assert np.abs(x4_s[ir].real - ref).max() < 1e-12 * scale, ir

@@ -46,6 +46,8 @@ SIGNATURES = {
     "isdf_pchol_workspace_bytes": [c_int, c_int, C.POINTER(c_size_t)],
     "isdf_pchol": [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_int, c_void_p, c_void_p,
                    c_void_p, c_void_p, c_void_p],
+    "isdf_pchol_real": [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                        c_void_p, c_void_p, c_void_p],
     "isdf_trsm_prepare": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                           c_void_p, c_void_p],
     "isdf_trsm_sweeps": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_long, c_long, c_int, c_void_p],

@@ -16,6 +16,7 @@
 // matrices of the batch concurrently) produces nb rows of U; the trailing update
 // A -= U_panel^H U_panel runs on the DMMA GEMM engine.
 #include <float.h>
+#include <type_traits>
 #include <cooperative_groups.h>
 #include "gemm_c128.cuh"
 
@@ -211,6 +212,9 @@ constexpr int PCC_NCOL = 2;      // columns per thread -> ncc <= 1024, n <= 8192
 
 struct PcCand { double v; int pos; int idx; };
 
+// REALP: the matrix is real (imaginary parts exactly zero, e.g. the selection matrix x4): the in-panel rows are
+// kept as doubles, which doubles the panel width that fits in shared memory (half as many trailing updates).
+template <bool REALP>
 __global__ void __cluster_dims__(PCC_CS, 1, 1) __launch_bounds__(PCC_THREADS, 1)
 pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n, int ncc, int j0, int nb,
                            int max_steps, double tol, cplx* Uall, long ldu, long strideU, int* posall,
@@ -225,7 +229,8 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
   int* pos = posall + (long)b * n;
 
   extern __shared__ __align__(16) unsigned char pcc_smem[];
-  cplx* up = reinterpret_cast<cplx*>(pcc_smem);                 // [nb][ncc] in-panel rows of U, own columns
+  typedef typename std::conditional<REALP, double, cplx>::type pan_t;
+  pan_t* up = reinterpret_cast<pan_t*>(pcc_smem);               // [nb][ncc] in-panel rows of U, own columns
   double* s_aii = reinterpret_cast<double*>(up + (long)nb * ncc);  // [ncc]
   __shared__ cplx bp[PC_NB_MAX];
   __shared__ PcCand cand[PCC_CS];
@@ -320,18 +325,7 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
         else if (mypos[c] == j) mypos[c] = ppos;
       }
     }
-    // ---- 4. owner CTA broadcasts the pivot column's in-panel entries to every CTA
-    const int owner = p / ncc;
-    if (crank == owner) {
-      const int pl = p - c_lo;
-      for (int w = tid; w < t * PCC_CS; w += PCC_THREADS) {
-        const int tt = w / PCC_CS, r = w - tt * PCC_CS;
-        cplx* remote = cluster.map_shared_rank(bp, r);
-        remote[tt] = up[(long)tt * ncc + pl];
-      }
-    }
-    cluster.sync();
-    // ---- 5. new row of U for the own columns
+    // ---- 4a. issue the loads of row p (lower triangle) now: their latency overlaps the broadcast + barrier
     const double rt = sqrt(dp);
     const double inv = 1.0 / rt;
     const cplx* Arow = A + (long)p * lda;
@@ -343,19 +337,36 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
       const int i = c_lo + lc;
       act[c] = (lc < ncc) && (i < n) && (i != p) && (mypos[c] > j);
       v[c] = make_double2(0.0, 0.0);
-      if (act[c]) {   // row p from the lower triangle
+      if (act[c]) {
         if (i < p) v[c] = Arow[i];
         else { const cplx w = A[(long)i * lda + p]; v[c] = make_double2(w.x, -w.y); }
       }
     }
+    // ---- 4b. owner CTA broadcasts the pivot column's in-panel entries to every CTA
+    const int owner = p / ncc;
+    if (crank == owner) {
+      const int pl = p - c_lo;
+      for (int w = tid; w < t * PCC_CS; w += PCC_THREADS) {
+        const int tt = w / PCC_CS, r = w - tt * PCC_CS;
+        cplx* remote = cluster.map_shared_rank(bp, r);
+        if constexpr (REALP) remote[tt] = make_double2(up[(long)tt * ncc + pl], 0.0);
+        else remote[tt] = up[(long)tt * ncc + pl];
+      }
+    }
+    cluster.sync();
+    // ---- 5. new row of U for the own columns
     for (int tt = 0; tt < t; ++tt) {
       const cplx bb = bp[tt];
 #pragma unroll
       for (int c = 0; c < PCC_NCOL; ++c) {
         if (act[c]) {
-          const cplx ui = up[(long)tt * ncc + tid + c * PCC_THREADS];
-          v[c].x -= bb.x * ui.x + bb.y * ui.y;   // v -= conj(bb) * ui
-          v[c].y -= bb.x * ui.y - bb.y * ui.x;
+          if constexpr (REALP) {
+            v[c].x -= bb.x * up[(long)tt * ncc + tid + c * PCC_THREADS];
+          } else {
+            const cplx ui = up[(long)tt * ncc + tid + c * PCC_THREADS];
+            v[c].x -= bb.x * ui.x + bb.y * ui.y;   // v -= conj(bb) * ui
+            v[c].y -= bb.x * ui.y - bb.y * ui.x;
+          }
         }
       }
     }
@@ -373,7 +384,10 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
         } else {
           u = make_double2(0.0, 0.0);
         }
-        if (t < nb) up[(long)t * ncc + lc] = u;
+        if (t < nb) {
+          if constexpr (REALP) up[(long)t * ncc + lc] = u.x;
+          else up[(long)t * ncc + lc] = u;
+        }
         U[(long)j * ldu + i] = u;
       }
     }
@@ -543,9 +557,25 @@ extern "C" int isdf_pchol_workspace_bytes(int n, int batch, size_t* bytes) {
 // trailing Schur complements.
 // u: [batch][ldu_rows][n] c128, rows j < rank hold row j of the factor A = U^H U in ORIGINAL column
 //    order (column piv[j] carries the pivot); must be zero-initialised by the caller? -> zeroed here.
+static int pchol_run(Handle* h, void* a, int n, int batch, int max_steps, double tol, int nb, void* u, int ldu_rows,
+                     int* piv, int* rank, double* next_pivot, void* workspace, void* stream, bool is_real);
+
 extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
                           int ldu_rows, int* piv, int* rank, double* next_pivot, void* workspace, void* stream) {
-  Handle* h = (Handle*)hv;
+  return pchol_run((Handle*)hv, a, n, batch, max_steps, tol, nb, u, ldu_rows, piv, rank, next_pivot, workspace, stream,
+                   false);
+}
+
+// Same as isdf_pchol for matrices whose imaginary parts are exactly zero (the selection matrix x4 of
+// isdf_select_gram): identical arithmetic, wider panels.
+extern "C" int isdf_pchol_real(void* hv, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
+                               int ldu_rows, int* piv, int* rank, double* next_pivot, void* workspace, void* stream) {
+  return pchol_run((Handle*)hv, a, n, batch, max_steps, tol, nb, u, ldu_rows, piv, rank, next_pivot, workspace, stream,
+                   true);
+}
+
+static int pchol_run(Handle* h, void* a, int n, int batch, int max_steps, double tol, int nb, void* u, int ldu_rows,
+                     int* piv, int* rank, double* next_pivot, void* workspace, void* stream, bool is_real) {
   cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, a && u && piv && rank && workspace, "null pointer");
   ISDF_CHECK_ARG(h, n >= 1 && n <= PC_THREADS * PC_NCOL, "n must be in [1, 8192]");
@@ -574,18 +604,25 @@ extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, do
   const int ncc = (n + PCC_CS - 1) / PCC_CS;
   size_t csmem = 0;
   if (use_cluster) {
+    const size_t esz = is_real ? sizeof(double) : sizeof(cplx);
     const long avail = 200 * 1024 - (long)ncc * (long)sizeof(double);
-    const int nb_fit = (int)(avail / ((long)ncc * (long)sizeof(cplx)));
+    const int nb_fit = (int)(avail / ((long)ncc * (long)esz));
     ISDF_CHECK_ARG(h, nb_fit >= 4 && ncc <= PCC_THREADS * PCC_NCOL, "matrix too large for the cluster panel kernel");
+    if (is_real && nb < PC_NB_MAX) nb = PC_NB_MAX;   // real panels: take the widest panel that fits
     if (nb > nb_fit) nb = nb_fit;
-    csmem = (size_t)nb * ncc * sizeof(cplx) + (size_t)ncc * sizeof(double);
-    ISDF_CUDA(h, cudaFuncSetAttribute(pchol_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+    csmem = (size_t)nb * ncc * esz + (size_t)ncc * sizeof(double);
+    if (is_real) ISDF_CUDA(h, cudaFuncSetAttribute(pchol_panel_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+    else ISDF_CUDA(h, cudaFuncSetAttribute(pchol_panel_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
   }
   // The panel that reaches max_steps also evaluates the would-be next pivot and sets the stop flag.
   for (int j0 = 0; j0 == 0 || j0 < max_steps; j0 += nb) {
     if (use_cluster) {
-      pchol_panel_cluster_kernel<<<dim3(PCC_CS, batch), PCC_THREADS, csmem, st>>>(
-          (const cplx*)a, n, strideA, n, ncc, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);
+      if (is_real)
+        pchol_panel_cluster_kernel<true><<<dim3(PCC_CS, batch), PCC_THREADS, csmem, st>>>(
+            (const cplx*)a, n, strideA, n, ncc, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);
+      else
+        pchol_panel_cluster_kernel<false><<<dim3(PCC_CS, batch), PCC_THREADS, csmem, st>>>(
+            (const cplx*)a, n, strideA, n, ncc, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);
     } else {
       pchol_panel_kernel<<<batch, PC_THREADS, (size_t)n * sizeof(double), st>>>(
           (const cplx*)a, n, strideA, n, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);

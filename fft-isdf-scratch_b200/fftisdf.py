@@ -606,7 +606,8 @@ class InterpolativeSeparableDensityFitting(_Base):
         assert x0.shape == (nkpt, ng, nao)                                                 # :374
         x4 = ops.select_gram(x0)                                                           # :376-379
         nmax = min(int(nao * c0), ng)
-        u, piv, rank, nxt = ops.pchol(x4.reshape(1, ng, ng), max_steps=nmax, tol=-1.0, nb=self.chol_nb)  # :381-382
+        u, piv, rank, nxt = ops.pchol(x4.reshape(1, ng, ng), max_steps=nmax, tol=-1.0, nb=self.chol_nb,
+                                      real=True)                                            # :381-382
         del u, x4
         comm = getattr(self, "comm", None)
         sharding.broadcast_(piv, 0, comm)   # every rank must use the same points (bitwise)

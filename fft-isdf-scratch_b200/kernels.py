@@ -51,8 +51,9 @@ class IsdfOps:
         return x4c
 
     # ---- K2/K5a: batched pivoted Cholesky ------------------------------------------------
-    def pchol(self, a, max_steps, tol=-1.0, nb=32):
-        """a: [batch, n, n] Hermitian PSD (destroyed).  Returns (u, piv, rank, next_pivot)."""
+    def pchol(self, a, max_steps, tol=-1.0, nb=32, real=False):
+        """a: [batch, n, n] Hermitian PSD (destroyed).  Returns (u, piv, rank, next_pivot).
+        real=True: imaginary parts are exactly zero (selection matrix) -> wider panels."""
         _chk(a, c128)
         batch, n, _ = a.shape
         ldu = max(1, max_steps)
@@ -63,9 +64,9 @@ class IsdfOps:
         nbytes = C.c_size_t()
         self.lib.isdf_pchol_workspace_bytes(n, batch, C.byref(nbytes))
         work = torch.empty((nbytes.value,), dtype=torch.uint8, device=self.device)
-        self.handle.check(self.lib.isdf_pchol(self.h, _ptr(a), n, batch, int(max_steps), float(tol), int(nb), _ptr(u),
-                                              ldu, _ptr(piv), _ptr(rank), _ptr(nxt), _ptr(work), _stream()),
-                          "isdf_pchol")
+        fn = self.lib.isdf_pchol_real if real else self.lib.isdf_pchol
+        self.handle.check(fn(self.h, _ptr(a), n, batch, int(max_steps), float(tol), int(nb), _ptr(u),
+                             ldu, _ptr(piv), _ptr(rank), _ptr(nxt), _ptr(work), _stream()), "isdf_pchol")
         npan = max(1, -(-max_steps // nb))
         self.launches += 3 + 2 * npan
         return u, piv, rank, nxt

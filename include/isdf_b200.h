@@ -44,6 +44,10 @@ int isdf_select_gram(void* handle, const void* x0, int nk, int n0, int nao, void
 int isdf_pchol_workspace_bytes(int n, int batch, size_t* bytes);
 int isdf_pchol(void* handle, void* a, int n, int batch, int max_steps, double tol, int nb, void* u, int ldu_rows,
                int* piv, int* rank, double* next_pivot, void* workspace, void* stream);
+/* Same for matrices whose imaginary parts are exactly zero (x4 of isdf_select_gram): identical arithmetic and
+ * pivots, in-panel rows kept as doubles so that twice as wide a panel fits (half the trailing updates). */
+int isdf_pchol_real(void* handle, void* a, int n, int batch, int max_steps, double tol, int nb, void* u, int ldu_rows,
+                    int* piv, int* rank, double* next_pivot, void* workspace, void* stream);
 
 /* fftisdf.py:38 (x2_k) and :76 (fx_k):  c[z][i][j] = sum_l conj(a[z][i][l]) * b[z][j][l]
  * a [m][k] (ld lda), b [n][k] (ld ldb), c [m][n] (ld ldc); batch strides in elements. */

@@ -18,7 +18,7 @@
 namespace isdf {
 
 enum { MODE_CONJA = 0, MODE_CONJB = 1, MODE_AB = 2 };  // conj(a)*b, a*conj(b), a*b
-enum { EPI_STORE = 0, EPI_SUB_HERM = 1, EPI_HERK = 2, EPI_SQ_SYM = 3, EPI_SUB_LOWER = 4 };
+enum { EPI_STORE = 0, EPI_HERK = 2, EPI_SQ_SYM = 3, EPI_SUB_LOWER = 4 };
 
 struct GemmParams {
   const cplx* A; long lda; long strideA;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
   using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW>;
   constexpr int LDA_S = S::LDA_S, LDB_S = S::LDB_S, A_TILE = S::A_TILE, B_TILE = S::B_TILE;
   constexpr int WARPS_N = BN / 16;
-  constexpr bool SYMM = (EPI == EPI_SUB_HERM || EPI == EPI_HERK || EPI == EPI_SQ_SYM || EPI == EPI_SUB_LOWER);
+  constexpr bool SYMM = (EPI == EPI_HERK || EPI == EPI_SQ_SYM || EPI == EPI_SUB_LOWER);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* sA = reinterpret_cast<cplx*>(smem_raw);
@@ -215,17 +215,6 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
         const double vi = REAL_ONLY ? 0.0 : acc_im[mi][ni][e];
         if (EPI == EPI_STORE) {
           Cb[(long)r * p.ldc + c] = make_double2(alpha * vr, alpha * vi);
-        } else if (EPI == EPI_SUB_HERM) {
-          if (r >= c) {
-            cplx* q = Cb + (long)r * p.ldc + c;
-            cplx o = *q;
-            *q = make_double2(o.x - vr, o.y - vi);
-            if (r > c) {
-              cplx* q2 = Cb + (long)c * p.ldc + r;
-              cplx o2 = *q2;
-              *q2 = make_double2(o2.x - vr, o2.y + vi);
-            }
-          }
         } else if (EPI == EPI_SUB_LOWER) {   // only the lower triangle is kept current (no mirrored traffic)
           if (r >= c) {
             cplx* q = Cb + (long)r * p.ldc + c;

@@ -435,7 +435,7 @@ def get_j_kpts_device(df_obj, dms):
     w0 = df_obj._wq_dev[0:1].contiguous()
     out = []
     for dm in dms:
-        d = torch.from_numpy(numpy.ascontiguousarray(dm)).to(ops.device)
+        d = torch.from_numpy(numpy.ascontiguousarray(dm, dtype=numpy.complex128)).to(ops.device)
         y = ops.gemm_nn(x, d)                                             # Y_k = X_k D_k
         rho = ops.rowdot_conj_sum(y, x, 1.0 / nk)                         # :155-156
         v = ops.gemm_nn(w0, rho.reshape(1, nip, 1).contiguous())          # :159  v = W_0 rho
@@ -459,7 +459,7 @@ def get_k_kpts_device(df_obj, dms):
     assert ok
     out = []
     for dm in dms:
-        d = torch.from_numpy(numpy.ascontiguousarray(dm)).to(ops.device)
+        d = torch.from_numpy(numpy.ascontiguousarray(dm, dtype=numpy.complex128)).to(ops.device)
         y = ops.gemm_nn(x, d)                                             # Y_k = X_k D_k
         g = ops.gram_conja(x, y)                                          # g[k][I][J] = rhok[k][J][I] * nk   (:211)
         vk_ip = torch.empty((nk, nip, nip), dtype=torch.complex128, device=ops.device)

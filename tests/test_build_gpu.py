@@ -250,8 +250,11 @@ def test_all_parent_points_selected_and_single_block():
     # nip is rank-limited here (A_q at the edge of numerical rank): check structure, not digits
     w = df._wq[0]
     assert np.isfinite(w).all() and np.abs(w - w.conj().T).max() == 0.0
-    vj, vk = df.get_jk(np.eye(3)[None] + 0j, kpts=df.kpts)
+    vj, vk = df.get_jk(np.eye(3)[None], kpts=df.kpts)          # real-dtype density matrix (common at Gamma)
+    df.jk_on_device = False
+    vj_h, vk_h = df.get_jk(np.eye(3)[None], kpts=df.kpts)
     assert np.isfinite(vj).all() and np.isfinite(vk).all()
+    assert rel(vj, vj_h) < 1e-10 and rel(vk, vk_h) < 1e-10
 
 
 def test_kmesh_metric_equals_supercell_pair_gram():

@@ -353,3 +353,21 @@ def test_dft3d_tensor_core_path(ops, mesh):
     ops.fft3d(d, mesh, nvec=nvec, ldv=ldv, mode="dmma")
     ref = np.fft.fftn(x[:, :ng].reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng)
     assert relerr(d.cpu().numpy()[:, :ng], ref) < 1e-13
+
+
+def test_cabi_error_conventions(ops):
+    """Status codes, never exceptions, across the ABI: < 0 argument error with a message in isdf_last_error."""
+    import ctypes as C
+    lib, h = ops.lib, ops.h
+    a = torch.zeros((1, 8, 8), dtype=torch.complex128, device="cuda")
+    rc = lib.isdf_pchol(h, C.c_void_p(a.data_ptr()), 8, 1, 8, C.c_double(-1.0), 999, C.c_void_p(a.data_ptr()), 8,
+                        C.c_void_p(a.data_ptr()), C.c_void_p(a.data_ptr()), None, C.c_void_p(a.data_ptr()), None)
+    assert rc < 0 and b"nb <= 64" in lib.isdf_last_error(h)
+    rc = lib.isdf_select_gram(h, None, 1, 8, 8, C.c_void_p(a.data_ptr()), None)
+    assert rc < 0 and b"null pointer" in lib.isdf_last_error(h)
+    m = (C.c_int * 3)(64, 5, 5)
+    rc = lib.isdf_dft3d_dmma(h, C.c_void_p(a.data_ptr()), 1, 1600, m, None, None, None)
+    assert rc == -2                                   # axis > 48: "use the Stockham entry point", nothing launched
+    with pytest.raises(Exception):
+        ops.fft3d(a.reshape(-1), [64, 5, 5], mode="dmma")
+    torch.cuda.synchronize()

@@ -232,8 +232,11 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
   typedef typename std::conditional<REALP, double, cplx>::type pan_t;
   pan_t* up = reinterpret_cast<pan_t*>(pcc_smem);               // [nb][ncc] in-panel rows of U, own columns
   double* s_aii = reinterpret_cast<double*>(up + (long)nb * ncc);  // [ncc]
-  __shared__ cplx bp[PC_NB_MAX];
-  __shared__ PcCand cand[PCC_CS];
+  // candidates and their in-panel columns, double-buffered by step parity: a CTA that runs one step ahead writes
+  // the other buffer, and it cannot run two steps ahead because of the per-step cluster barrier
+  __shared__ cplx bpc[2][PCC_CS][PC_NB_MAX];
+  __shared__ PcCand cand[2][PCC_CS];
+  __shared__ int s_best;                    // this CTA's candidate column (global index), -1 if none
   __shared__ double red_v[PCC_THREADS / 32];
   __shared__ int red_pos[PCC_THREADS / 32];
   __shared__ int red_idx[PCC_THREADS / 32];
@@ -292,8 +295,23 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
         if (ov > bv || (ov == bv && op < bpos)) { bv = ov; bpos = op; bidx = oi; }
       }
       if (lane < PCC_CS) {   // lane r publishes this CTA's candidate into CTA r's table
-        PcCand* remote = cluster.map_shared_rank(cand, lane);
-        remote[crank].v = bv; remote[crank].pos = bpos; remote[crank].idx = bidx;
+        PcCand (*remote)[PCC_CS] = cluster.map_shared_rank(cand, lane);
+        remote[t & 1][crank].v = bv; remote[t & 1][crank].pos = bpos; remote[t & 1][crank].idx = bidx;
+      }
+      if (lane == 0) s_best = bidx;
+    }
+    __syncthreads();
+    // publish the candidate's in-panel column next to it, so that ONE cluster barrier per step suffices: after it
+    // every CTA knows the winner and already holds the winner's column u_{0..t-1, p}
+    {
+      const int bl = s_best - c_lo;
+      if (s_best >= 0) {
+        for (int w = tid; w < t * PCC_CS; w += PCC_THREADS) {
+          const int tt = w / PCC_CS, r = w - tt * PCC_CS;
+          cplx (*remote)[PCC_CS][PC_NB_MAX] = cluster.map_shared_rank(bpc, r);
+          if constexpr (REALP) remote[t & 1][crank][tt] = make_double2(up[(long)tt * ncc + bl], 0.0);
+          else remote[t & 1][crank][tt] = up[(long)tt * ncc + bl];
+        }
       }
     }
     cluster.sync();
@@ -302,8 +320,8 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
     int ppos = 0x7fffffff, p = -1;
 #pragma unroll
     for (int r = 0; r < PCC_CS; ++r) {
-      const double ov = cand[r].v;
-      const int op = cand[r].pos, oi = cand[r].idx;
+      const double ov = cand[t & 1][r].v;
+      const int op = cand[t & 1][r].pos, oi = cand[t & 1][r].idx;
       if (ov > dp || (ov == dp && op < ppos)) { dp = ov; ppos = op; p = oi; }
     }
     if (j == 0) dstop = (tol < 0.0) ? (double)n * DBL_EPSILON * dp : tol;
@@ -342,18 +360,8 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
         else { const cplx w = A[(long)i * lda + p]; v[c] = make_double2(w.x, -w.y); }
       }
     }
-    // ---- 4b. owner CTA broadcasts the pivot column's in-panel entries to every CTA
-    const int owner = p / ncc;
-    if (crank == owner) {
-      const int pl = p - c_lo;
-      for (int w = tid; w < t * PCC_CS; w += PCC_THREADS) {
-        const int tt = w / PCC_CS, r = w - tt * PCC_CS;
-        cplx* remote = cluster.map_shared_rank(bp, r);
-        if constexpr (REALP) remote[tt] = make_double2(up[(long)tt * ncc + pl], 0.0);
-        else remote[tt] = up[(long)tt * ncc + pl];
-      }
-    }
-    cluster.sync();
+    // ---- 4b. the winner's column arrived with its candidate
+    const cplx* bp = bpc[t & 1][p / ncc];
     // ---- 5. new row of U for the own columns
     for (int tt = 0; tt < t; ++tt) {
       const cplx bb = bp[tt];
@@ -392,7 +400,8 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
       }
     }
     steps_done = t + 1;
-    __syncthreads();   // up[t][*] visible to the owner's broadcast of the next step
+    // no barrier here: up[t][*] is ordered before the next step's publish by that step's block barrier, and the
+    // cand/bpc buffers of this step are not overwritten before the next-but-one step (double buffering)
   }
 #pragma unroll
   for (int c = 0; c < PCC_NCOL; ++c) {

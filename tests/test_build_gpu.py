@@ -57,6 +57,14 @@ def test_full_rank_cases_match_reference(name, tol_w, tol_jk):
     ex_ref = O.exchange_energy(g["vk"].reshape(shp), g["dm"].reshape(shp))
     ex = O.exchange_energy(np.asarray(vk).reshape(shp), g["dm"].reshape(shp))
     assert abs(ex - ex_ref) < tol_jk * abs(ex_ref)
+    # reconstructed ERIs (fftdf-with-k-lstsq.py:232) from the GPU W_q vs from the reference's W_q
+    x = g["x"]
+    nk = len(x)
+    for (k1, k2, k3) in [(0, 0, 0), (0, nk - 1, 0), (nk // 2, 0, nk - 1)]:
+        for q in range(nk):
+            e_gpu = O.eri_from_w(df._wq[q], x[k1], x[k2], x[k3], x[k1])
+            e_ref = O.eri_from_w(g["wq"][q], x[k1], x[k2], x[k3], x[k1])
+            assert rel(e_gpu, e_ref) < tol_w
     # Theta against the oracle's gelsy solution
     out = O.build(g["a"], g["kpts"], g["kmesh"].tolist(), g["mesh"].tolist(), g["x0"], g["f_all"], g["coord"],
                   float(g["c0"]), keep_theta=True)

@@ -50,7 +50,7 @@ SIGNATURES = {
                         c_void_p, c_void_p, c_void_p],
     "isdf_trsm_prepare": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                           c_void_p, c_void_p],
-    "isdf_trsm_sweeps": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_long, c_long, c_int, c_void_p],
+    "isdf_trsm_sweeps": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_long, c_int, c_void_p],
     "isdf_ktransform_square": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_long, c_long, c_int,
                                c_int, P_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_long, c_void_p, c_void_p],
     "isdf_fft3d_batched": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_long, c_void_p],

@@ -4,12 +4,20 @@
 // staged global -> shared with a cp.async (LDGSTS) ring; each lane pulls one complex
 // element per fragment with a single conflict-free LDS.128 and feeds the re/im halves to the
 // FP64 tensor pipe (mma.sync.m8n8k4.f64 == DMMA.8x8x4, the only FP64 MMA sm_100a has; tcgen05
-// has no f64 kind).  One complex MAC = 4 DMMA lanes-worth of FMAs (the "4M" form).
+// has no f64 kind).
 //
-// Default configuration (measured best on B200, profiles/r1_gemm_variants.txt): CTA tile 64x64 complex,
-// 256 threads = 8 warps of 32(m) x 16(n), K step 16 complex, 2-stage cp.async ring, TWO CTAs per SM so
-// that one CTA's barrier / prologue / epilogue bubbles are filled by the other (92 % of cuBLAS DGEMM).
-// ISDF_GEMM_SMALL=0 selects the 512-thread 128x64 / 64x128 tiles (one CTA per SM, 86 %).
+// Complex products use the 3M (Karatsuba) form by default: with P1 = sum ar*br, P2 = sum ai*bi and
+// P3 = sum (ar+ai)(br+bi), re = P1 - P2 and im = P3 - P1 - P2 -- three real MMAs per complex MAC instead of
+// four, i.e. 25 % less work on the pipe that bounds every dense stage (the two extra additions per
+// fragment element are noise).  The error is bounded normwise, ~2x the 4M constant, which is what the
+// 1e-10 parity budget is stated in.  ISDF_GEMM_3M=0 builds the classical 4M form.  Real-only products
+// (selection Gram) need two MMAs either way.
+//
+// Default configuration (measured on B200, profiles/r1_gemm_variants.txt): 256 threads, K step 16 complex,
+// 2-stage cp.async ring, TWO CTAs per SM so that one CTA's barrier / prologue / epilogue bubbles are filled
+// by the other.  4M: CTA tile 64x64, 8 warps of 32(m) x 16(n) (92 % of cuBLAS DGEMM).  3M keeps three
+// accumulator sets, so the warp tile is 16 x 16 and the CTA tile 64x32 to stay within 128 registers.
+// ISDF_GEMM_SMALL=0 selects the 512-thread 128x64 / 64x128 4M tiles (one CTA per SM, 86 %).
 //
 // Operand layouts: KCONTIG = [rows][K] row-major (K fastest), KSLOW = [K][rows] (rows fastest).
 #pragma once
@@ -33,7 +41,10 @@ struct GemmParams {
 };
 
 #ifndef ISDF_GEMM_BK
-#define ISDF_GEMM_BK 16
+#define ISDF_GEMM_BK 16       // complex K elements per pipeline stage of the 4M / real-only kernels
+#endif
+#ifndef ISDF_GEMM_3M_BK
+#define ISDF_GEMM_3M_BK 32    // ... of the 3M kernels (64x32 tiles: 2 x 54 KB per CTA, still two CTAs per SM)
 #endif
 #ifndef ISDF_GEMM_STAGES
 #define ISDF_GEMM_STAGES 2
@@ -41,26 +52,61 @@ struct GemmParams {
 #ifndef ISDF_GEMM_SMALL
 #define ISDF_GEMM_SMALL 1     // 1: 64x64 tiles, 256 threads, 2 CTAs per SM; 0: 128x64 / 64x128 tiles, 512 threads
 #endif
-constexpr int GEMM_BK = ISDF_GEMM_BK;        // complex K elements per pipeline stage (multiple of 4)
+#ifndef ISDF_GEMM_3M
+#define ISDF_GEMM_3M 1        // 1: Karatsuba complex product (3 DMMA per complex MAC); 0: classical 4
+#endif
+#ifndef ISDF_GEMM_3M_BM
+#define ISDF_GEMM_3M_BM 64    // CTA tile of the 3M kernels (warp tile 16x16)
+#endif
+#ifndef ISDF_GEMM_3M_BN
+#define ISDF_GEMM_3M_BN 32
+#endif
 constexpr int GEMM_STAGES = ISDF_GEMM_STAGES;
-__host__ __device__ constexpr int gemm_threads(int BM, int BN) { return (BM / 32) * (BN / 16) * 32; }
-__host__ __device__ constexpr int gemm_min_blocks(int BM, int BN) { return gemm_threads(BM, BN) <= 256 ? 2 : 1; }
+__host__ __device__ constexpr bool gemm_is_3m(bool real_only) { return ISDF_GEMM_3M != 0 && !real_only; }
+__host__ __device__ constexpr int gemm_bk(bool real_only) {   // multiple of 4
+  return gemm_is_3m(real_only) ? ISDF_GEMM_3M_BK : ISDF_GEMM_BK;
+}
+#ifndef ISDF_GEMM_WM_3M
+#define ISDF_GEMM_WM_3M 16    // warp tile rows of the 3M kernels (tuning)
+#endif
+#ifndef ISDF_GEMM_WM_4M
+#define ISDF_GEMM_WM_4M 32
+#endif
+#ifndef ISDF_GEMM_4M_BN
+#define ISDF_GEMM_4M_BN 64
+#endif
+#ifndef ISDF_GEMM_MINB
+#define ISDF_GEMM_MINB 2      // resident CTAs per SM asked of the compiler for <= 256-thread tiles
+#endif
+__host__ __device__ constexpr int gemm_wm(bool real_only) {   // warp tile rows
+  return gemm_is_3m(real_only) ? ISDF_GEMM_WM_3M : (real_only ? 32 : ISDF_GEMM_WM_4M);
+}
+__host__ __device__ constexpr int gemm_threads(int BM, int BN, bool real_only) {
+  return (BM / gemm_wm(real_only)) * (BN / 16) * 32;
+}
+__host__ __device__ constexpr int gemm_min_blocks(int BM, int BN, bool real_only) {
+  return gemm_threads(BM, BN, real_only) <= 256 ? ISDF_GEMM_MINB : 1;
+}
 
-template <int BM, int BN, bool A_KSLOW, bool B_KSLOW>
+template <int BM, int BN, bool A_KSLOW, bool B_KSLOW, int BK>
 struct GemmSmem {
-  static constexpr int LDA_S = A_KSLOW ? (BM + 2) : (GEMM_BK + 4);
-  static constexpr int LDB_S = B_KSLOW ? (BN + 2) : (GEMM_BK + 4);
-  static constexpr int A_TILE = A_KSLOW ? GEMM_BK * LDA_S : BM * LDA_S;
-  static constexpr int B_TILE = B_KSLOW ? GEMM_BK * LDB_S : BN * LDB_S;
+  static constexpr int LDA_S = A_KSLOW ? (BM + 2) : (BK + 4);
+  static constexpr int LDB_S = B_KSLOW ? (BN + 2) : (BK + 4);
+  static constexpr int A_TILE = A_KSLOW ? BK * LDA_S : BM * LDA_S;
+  static constexpr int B_TILE = B_KSLOW ? BK * LDB_S : BN * LDB_S;
   static constexpr int BYTES = GEMM_STAGES * (A_TILE + B_TILE) * (int)sizeof(cplx);
 };
 
 template <int BM, int BN, bool A_KSLOW, bool B_KSLOW, int MODE, bool REAL_ONLY, int EPI>
-__global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN)) gemm_c128_kernel(GemmParams p) {
-  static_assert(BM % 32 == 0 && BN % 16 == 0, "warp tile is 32x16");
-  constexpr int GEMM_THREADS = gemm_threads(BM, BN);
-  constexpr int BK = GEMM_BK, STAGES = GEMM_STAGES;
-  using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW>;
+__global__ void __launch_bounds__(gemm_threads(BM, BN, REAL_ONLY), gemm_min_blocks(BM, BN, REAL_ONLY))
+    gemm_c128_kernel(GemmParams p) {
+  constexpr bool K3M = gemm_is_3m(REAL_ONLY);
+  constexpr int WM = gemm_wm(REAL_ONLY), MI = WM / 8;     // warp tile WM x 16 = MI x 2 DMMA tiles
+  static_assert(BM % WM == 0 && BN % 16 == 0, "warp tile is WM x 16");
+  constexpr int GEMM_THREADS = gemm_threads(BM, BN, REAL_ONLY);
+  static_assert(GEMM_THREADS <= 1024, "CTA tile too large for this warp tile");
+  constexpr int BK = gemm_bk(REAL_ONLY), STAGES = GEMM_STAGES;
+  using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW, BK>;
   constexpr int LDA_S = S::LDA_S, LDB_S = S::LDB_S, A_TILE = S::A_TILE, B_TILE = S::B_TILE;
   constexpr int WARPS_N = BN / 16;
   constexpr bool SYMM = (EPI == EPI_HERK || EPI == EPI_SQ_SYM || EPI == EPI_SUB_LOWER);
@@ -78,7 +124,7 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp / WARPS_N) * 32, wn0 = (warp % WARPS_N) * 16;
+  const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * 16;
   const int M = p.M, N = p.N;
   int K = p.K;
   const cplx* Abase = p.A + (long)bz * p.strideA;
@@ -92,6 +138,9 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
   }
   const int ktiles = (K + BK - 1) / BK;
   const int nit = p.nseg * ktiles;
+  // Ragged edges cost what they use: a warp whose block has no valid row/column (or, for the symmetric
+  // epilogues, lies strictly above the diagonal) still helps stage the tiles but issues no DMMA.
+  const bool warp_live = (m0 + wm0 < M) && (n0 + wn0 < N) && !(SYMM && n0 + wn0 > m0 + wm0 + WM - 1);
 
   auto load_tiles = [&](int it, int slot) {
     const int seg = it / ktiles;
@@ -136,14 +185,17 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
     }
   };
 
-  double acc_re[4][2][2];
-  double acc_im[REAL_ONLY ? 1 : 4][2][2];
+  // 4M: acc_re / acc_im.  3M: acc_re = P1 = sum ar*br, acc_im = P2 = sum ai*bi, acc_p3 = sum (ar +- ai)(br +- bi)
+  double acc_re[MI][2][2];
+  double acc_im[REAL_ONLY ? 1 : MI][2][2];
+  double acc_p3[K3M ? MI : 1][2][2];
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) {
       acc_re[mi][ni][0] = 0.0; acc_re[mi][ni][1] = 0.0;
       if (!REAL_ONLY) { acc_im[mi][ni][0] = 0.0; acc_im[mi][ni][1] = 0.0; }
+      if (K3M) { acc_p3[mi][ni][0] = 0.0; acc_p3[mi][ni][1] = 0.0; }
     }
 
 #pragma unroll
@@ -160,36 +212,64 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
       if (nx < nit) load_tiles(nx, nx % STAGES);
       cp_async_commit();
     }
+    if (!warp_live) continue;   // warp-uniform: this warp's block lies outside M x N (or above the diagonal)
     const cplx* tA = sA + (it % STAGES) * A_TILE;
     const cplx* tB = sB + (it % STAGES) * B_TILE;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
-      cplx a[4], b[2];
+      cplx a[MI], b[2];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+      for (int mi = 0; mi < MI; ++mi)
         a[mi] = A_KSLOW ? tA[(ks * 4 + t) * LDA_S + wm0 + mi * 8 + g] : tA[(wm0 + mi * 8 + g) * LDA_S + ks * 4 + t];
 #pragma unroll
       for (int ni = 0; ni < 2; ++ni)
         b[ni] = B_KSLOW ? tB[(ks * 4 + t) * LDB_S + wn0 + ni * 8 + g] : tB[(wn0 + ni * 8 + g) * LDB_S + ks * 4 + t];
+      if constexpr (K3M) {
+        // conj(a) b: (ar - ai)(br + bi);  a conj(b): (ar + ai)(br - bi);  a b: (ar + ai)(br + bi)
+        double as[MI], bs[2];
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        const double br = b[ni].x, bi = b[ni].y;
-        const double nbr = -br, nbi = -bi;
+        for (int mi = 0; mi < MI; ++mi)
+#ifdef ISDF_GEMM_DIAG_NOSUM   // timing diagnostic only (wrong results): how much do the DADDs cost?
+          as[mi] = a[mi].x;
+#else
+          as[mi] = (MODE == MODE_CONJA) ? a[mi].x - a[mi].y : a[mi].x + a[mi].y;
+#endif
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-          const double ar = a[mi].x, ai = a[mi].y;
-          dmma884(acc_re[mi][ni][0], acc_re[mi][ni][1], ar, br);
-          dmma884(acc_re[mi][ni][0], acc_re[mi][ni][1], ai, (MODE == MODE_AB) ? nbi : bi);
-          if (!REAL_ONLY) {
-            if (MODE == MODE_CONJA) {         // im = ar*bi - ai*br
-              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, bi);
-              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, nbr);
-            } else if (MODE == MODE_CONJB) {  // im = ai*br - ar*bi
-              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, br);
-              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, nbi);
-            } else {                          // im = ar*bi + ai*br
-              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, bi);
-              dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, br);
+        for (int ni = 0; ni < 2; ++ni)
+#ifdef ISDF_GEMM_DIAG_NOSUM
+          bs[ni] = b[ni].y;
+#else
+          bs[ni] = (MODE == MODE_CONJB) ? b[ni].x - b[ni].y : b[ni].x + b[ni].y;
+#endif
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int mi = 0; mi < MI; ++mi) {
+            dmma884(acc_re[mi][ni][0], acc_re[mi][ni][1], a[mi].x, b[ni].x);
+            dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], a[mi].y, b[ni].y);
+            dmma884(acc_p3[mi][ni][0], acc_p3[mi][ni][1], as[mi], bs[ni]);
+          }
+      } else {
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+          const double br = b[ni].x, bi = b[ni].y;
+          const double nbr = -br, nbi = -bi;
+#pragma unroll
+          for (int mi = 0; mi < MI; ++mi) {
+            const double ar = a[mi].x, ai = a[mi].y;
+            dmma884(acc_re[mi][ni][0], acc_re[mi][ni][1], ar, br);
+            dmma884(acc_re[mi][ni][0], acc_re[mi][ni][1], ai, (MODE == MODE_AB) ? nbi : bi);
+            if (!REAL_ONLY) {
+              if (MODE == MODE_CONJA) {         // im = ar*bi - ai*br
+                dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, bi);
+                dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, nbr);
+              } else if (MODE == MODE_CONJB) {  // im = ai*br - ar*bi
+                dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, br);
+                dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, nbi);
+              } else {                          // im = ar*bi + ai*br
+                dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ar, bi);
+                dmma884(acc_im[mi][ni][0], acc_im[mi][ni][1], ai, br);
+              }
             }
           }
         }
@@ -202,7 +282,7 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
   const int* perm = (EPI == EPI_HERK && p.perm != nullptr) ? p.perm + (long)bz * p.stridePerm : nullptr;
   const double alpha = p.alpha;
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi) {
+  for (int mi = 0; mi < MI; ++mi) {
     const int r = m0 + wm0 + mi * 8 + g;
     if (r >= M) continue;
 #pragma unroll
@@ -211,8 +291,13 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
       for (int e = 0; e < 2; ++e) {
         const int c = n0 + wn0 + ni * 8 + 2 * t + e;
         if (c >= N) continue;
-        const double vr = acc_re[mi][ni][e];
-        const double vi = REAL_ONLY ? 0.0 : acc_im[mi][ni][e];
+        double vr = acc_re[mi][ni][e];
+        double vi = REAL_ONLY ? 0.0 : acc_im[mi][ni][e];
+        if (K3M) {
+          const double p1 = vr, p2 = vi, p3 = acc_p3[mi][ni][e];
+          if (MODE == MODE_AB) { vr = p1 - p2; vi = (p3 - p1) - p2; }
+          else                 { vr = p1 + p2; vi = (p3 - p1) + p2; }
+        }
         if (EPI == EPI_STORE) {
           Cb[(long)r * p.ldc + c] = make_double2(alpha * vr, alpha * vi);
         } else if (EPI == EPI_SUB_LOWER) {   // only the lower triangle is kept current (no mirrored traffic)
@@ -242,9 +327,10 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN), gemm_min_blocks(BM, BN))
 
 template <int BM_, int BN_, bool A_KSLOW, bool B_KSLOW, int MODE, bool REAL_ONLY, int EPI>
 inline cudaError_t launch_gemm(const GemmParams& p, int batch, cudaStream_t st) {
-  constexpr int BM = ISDF_GEMM_SMALL ? 64 : BM_;
-  constexpr int BN = ISDF_GEMM_SMALL ? 64 : BN_;
-  using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW>;
+  constexpr bool K3M = gemm_is_3m(REAL_ONLY);
+  constexpr int BM = K3M ? ISDF_GEMM_3M_BM : (ISDF_GEMM_SMALL ? 64 : BM_);
+  constexpr int BN = K3M ? ISDF_GEMM_3M_BN : (ISDF_GEMM_SMALL ? (REAL_ONLY ? 64 : ISDF_GEMM_4M_BN) : BN_);
+  using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW, gemm_bk(REAL_ONLY)>;
   auto kern = gemm_c128_kernel<BM, BN, A_KSLOW, B_KSLOW, MODE, REAL_ONLY, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -254,7 +340,7 @@ inline cudaError_t launch_gemm(const GemmParams& p, int batch, cudaStream_t st) 
   }
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch * (p.ksplit > 1 ? p.ksplit : 1));
-  kern<<<grid, gemm_threads(BM, BN), S::BYTES, st>>>(p);
+  kern<<<grid, gemm_threads(BM, BN, REAL_ONLY), S::BYTES, st>>>(p);
   return cudaGetLastError();
 }
 

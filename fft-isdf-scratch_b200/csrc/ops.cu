@@ -215,7 +215,7 @@ extern "C" int isdf_herk_scatter(void* hv, const void* b, long ldb, long strideB
   }
   p.C = (cplx*)h->scratch; p.ldc = n; p.strideC = (long)n * n;
   p.perm = nullptr; p.stridePerm = 0; p.alpha = 1.0;
-  p.ksplit = ksplit; p.kchunk = ((k + ksplit - 1) / ksplit + 15) / 16 * 16; p.strideSplit = (long)batch * n * n;
+  p.ksplit = ksplit; p.kchunk = ((k + ksplit - 1) / ksplit + 31) / 32 * 32; p.strideSplit = (long)batch * n * n;
   ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_HERK>(p, batch, st)));
   dim3 grid((n + 15) / 16, (n + 15) / 16, batch), block(16, 16);
   herk_splitk_reduce_kernel<<<grid, block, 0, st>>>((const cplx*)h->scratch, ksplit, p.strideSplit, n, alpha, perm,

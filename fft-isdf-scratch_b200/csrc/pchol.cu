@@ -693,32 +693,38 @@ extern "C" int isdf_trsm_prepare(void* hv, const void* u, int ldu_rows, const in
 }
 
 // In-place blocked substitution  T <- U^{-1} U^{-H} T  on T[batch][nP][ng] (row-major, ng contiguous).
-extern "C" int isdf_trsm_sweeps(void* hv, const void* lfwd, const void* ubwd, void* t, int nP, long ng, long ldt,
-                                int batch, void* stream) {
+// Only the first nact rows (nact >= every batch member's rank) are touched: rows at and beyond the rank are
+// zero on input and stay zero, so neither their block rows nor their K range are executed.
+extern "C" int isdf_trsm_sweeps(void* hv, const void* lfwd, const void* ubwd, void* t, int nP, int nact, long ng,
+                                long ldt, int batch, void* stream) {
   Handle* h = (Handle*)hv;
   cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, lfwd && ubwd && t, "null pointer");
   ISDF_CHECK_ARG(h, nP % TB == 0 && ng >= 1 && ng < (1L << 31) && ldt >= ng, "shape");
-  const int nblk = nP / TB;
+  ISDF_CHECK_ARG(h, nact >= 0 && nact <= nP, "nact out of range");
+  if (nact == 0) return ISDF_OK;
+  const int nblk = (nact + TB - 1) / TB;
   GemmParams p;
   p.lda = nP; p.strideA = (long)nP * nP;
   p.ldb = ldt; p.strideB = (long)nP * ldt;
   p.ldc = ldt; p.strideC = (long)nP * ldt;
-  p.M = TB; p.N = (int)ng;
+  p.N = (int)ng;
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
   p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
   for (int a = 0; a < nblk; ++a) {  // forward: rows 0..a
     p.A = (const cplx*)lfwd + (long)a * TB * nP;
     p.B = (const cplx*)t;
     p.C = (cplx*)t + (long)a * TB * ldt;
-    p.K = (a + 1) * TB;
+    p.M = (nact - a * TB < TB) ? (nact - a * TB) : TB;
+    p.K = ((a + 1) * TB < nact) ? (a + 1) * TB : nact;
     ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st)));
   }
   for (int a = nblk - 1; a >= 0; --a) {  // backward: rows a..end
     p.A = (const cplx*)ubwd + (long)a * TB * nP + (long)a * TB;
     p.B = (const cplx*)t + (long)a * TB * ldt;
     p.C = (cplx*)t + (long)a * TB * ldt;
-    p.K = nP - a * TB;
+    p.M = (nact - a * TB < TB) ? (nact - a * TB) : TB;
+    p.K = nact - a * TB;
     ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st)));
   }
   return ISDF_OK;

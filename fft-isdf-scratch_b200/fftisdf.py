@@ -289,7 +289,8 @@ def build(df_obj):
     # ---- C(b). Theta_q = A_q^+ Y_q^T by two blocked triangular sweeps, all q at once  :108
     lfwd, ubwd = lfwd_g.result(), ubwd_g.result()
     del lfwd_g, ubwd_g
-    ops.trsm_sweeps(lfwd, ubwd, theta)
+    rmax = int(rank_h.max())
+    ops.trsm_sweeps(lfwd, ubwd, theta, nact=rmax)     # rows at positions >= max rank are zero and stay zero
     del lfwd, ubwd
     mark("fit")
     if getattr(df_obj, "keep_theta", False):
@@ -307,13 +308,16 @@ def build(df_obj):
     if p2p:
         # fused exchange: each rank transforms its nipP/world vectors of every q, reading the planes from and
         # writing the result to the ranks' column shards over NVLink inside the DFT kernels
-        nv = nipP // world
-        work = torch.empty((nv, ngrid), dtype=torch.complex128, device=dev)
+        # (rows at positions >= max rank are identically zero: only the live rows are dealt out)
+        nv = -(-rmax // world)
+        v_lo = rank * nv
+        v_cnt = max(0, min(nv, rmax - v_lo))
+        work = torch.empty((max(v_cnt, 1), ngrid), dtype=torch.complex128, device=dev)
         peerbuf.barrier()                                    # every rank's Theta shard is complete
         for s, q in enumerate(qind):                                              # :97
             ops.phase_table(coord_d, vk[q], fq_d)                                 # :99
             ops.coulomb_weights(bvec, kscaled[q], mesh, vol, wgt_d)               # :114-115
-            ops.dft3d_p2p(peerbuf.ptrs, ncol, s * nipP + rank * nv, work, nv, mesh, pre=fq_d, post=wgt_d)
+            ops.dft3d_p2p(peerbuf.ptrs, ncol, s * nipP + v_lo, work, v_cnt, mesh, pre=fq_d, post=wgt_d)
         peerbuf.barrier()                                    # all scatters have landed
         del work
         mark("fft")
@@ -332,7 +336,7 @@ def build(df_obj):
         theta = sharding.to_column_layout(vecs, comm)            # [nq][nipP][ncol]
         del vecs
     wslot = torch.zeros((nq, nip, nip), dtype=torch.complex128, device=dev)
-    nrow = min(nip, nipP)
+    nrow = min(nip, rmax)
     ops.herk_strided(theta, ncol, nipP * ncol, nrow, ncol, 1.0, piv_q, nip, wslot, nip, nip * nip, nq)   # :121
     sharding.allreduce_sum_(wslot, comm)
     wq = torch.empty((nkpt, nip, nip), dtype=torch.complex128, device=dev)

@@ -206,12 +206,14 @@ class IsdfOps:
         self.launches += 3
         return lfwd, ubwd
 
-    def trsm_sweeps(self, lfwd, ubwd, t):
+    def trsm_sweeps(self, lfwd, ubwd, t, nact=None):
+        """nact: rows of t that can be non-zero (>= every rank in the batch); the rest is neither read nor written."""
         _chk(t, c128)
         batch, nP, ng = t.shape
-        self.handle.check(self.lib.isdf_trsm_sweeps(self.h, _ptr(lfwd), _ptr(ubwd), _ptr(t), nP, ng, ng, batch,
+        nact = nP if nact is None else int(nact)
+        self.handle.check(self.lib.isdf_trsm_sweeps(self.h, _ptr(lfwd), _ptr(ubwd), _ptr(t), nP, nact, ng, ng, batch,
                                                     _stream()), "isdf_trsm_sweeps")
-        self.launches += 2 * (nP // TB)
+        self.launches += 2 * (-(-nact // TB))
 
     # ---- K6: batched 3-D FFT with fused phase / weight ----------------------------------------
     @staticmethod
@@ -243,8 +245,7 @@ class IsdfOps:
             assert fits, "dmma DFT needs every mesh axis in [2, 48]"
             self.handle.check(self.lib.isdf_dft3d_dmma(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
                                                        _stream()), "isdf_dft3d_dmma")
-            gv = max(1, int(64 * 1024 * 1024 / (ng * 16)))
-            self.launches += 2 * (-(-nvec // gv))
+            self.launches += 2 if nvec > 0 else 0       # one zy launch + one x launch for the whole batch
             return
         self.handle.check(self.lib.isdf_fft3d_batched(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
                                                       int(group_vecs), _stream()), "isdf_fft3d_batched")
@@ -259,9 +260,7 @@ class IsdfOps:
         self.handle.check(self.lib.isdf_dft3d_dmma_p2p(self.h, arr, world, int(ncol), int(row0), _ptr(work), int(nvec),
                                                        work.shape[-1], m, _ptr(pre), _ptr(post), _stream()),
                           "isdf_dft3d_dmma_p2p")
-        ng = int(np.prod(mesh))
-        gv = max(1, int(64 * 1024 * 1024 / (ng * 16)))
-        self.launches += 2 * (-(-nvec // gv))
+        self.launches += 2 if nvec > 0 else 0
 
     # ---- K7: W = alpha * B B^H, scattered through perm -------------------------------------------
     def herk(self, b, alpha=1.0, perm=None, out=None):

@@ -108,7 +108,7 @@ int isdf_scale_rows(void* handle, const void* x, const void* v, int nz, int nrow
 int isdf_trsm_prepare(void* handle, const void* u, int ldu_rows, const int* piv, const int* rank, int n, int nP,
                       int batch, void* lfwd, void* ubwd, void* work, void* stream);
 /* In place T <- U^{-1} U^{-H} T on t [batch][nP][ldt] (ng columns used): Theta in pivot order. */
-int isdf_trsm_sweeps(void* handle, const void* lfwd, const void* ubwd, void* t, int nP, long ng, long ldt, int batch,
+int isdf_trsm_sweeps(void* handle, const void* lfwd, const void* ubwd, void* t, int nP, int nact, long ng, long ldt, int batch,
                      void* stream);
 
 /* fftisdf.py:113-115  pbctools.fft(z_q * fq, mesh) * coulG * vol/ngrid  (the ifft at :118 is removed by

@@ -119,8 +119,9 @@ def test_pchol_early_stop_and_zero_steps(ops):
     assert int(rank.cpu()[0]) == 0
 
 
-@pytest.mark.parametrize("n,ng", [(100, 517), (64, 128), (200, 1000)])
-def test_trsm_solve(ops, n, ng):
+@pytest.mark.parametrize("trim", [False, True])
+@pytest.mark.parametrize("n,ng", [(100, 517), (64, 128), (200, 1000), (157, 333)])
+def test_trsm_solve(ops, n, ng, trim):
     rng = np.random.default_rng(8)
     batch = 2
     a = np.stack([_psd(rng, n, n + 20) + 0.1 * np.eye(n) for _ in range(batch)])
@@ -133,7 +134,8 @@ def test_trsm_solve(ops, n, ng):
     for z in range(batch):
         t[z, :n] = y[z][pivh[z]]
     td = dev(t)
-    ops.trsm_sweeps(lfwd, ubwd, td)
+    # trim: only the first n rows (>= every rank) are swept; the padding rows are neither read nor written
+    ops.trsm_sweeps(lfwd, ubwd, td, nact=n if trim else None)
     sol = td.cpu().numpy()
     for z in range(batch):
         ref = np.linalg.solve(a[z], y[z])

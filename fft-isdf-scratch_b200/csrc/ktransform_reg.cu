@@ -1,5 +1,5 @@
 // Register-resident variant of the k<->R transform / square / k<->R transform for small k-meshes
-// (every axis <= 4): one thread (nk <= 32) or four lanes (nk <= 64) own all nk values of one element, so there is no shared
+// (every axis <= 4): one thread (nk < 27) or three / four lanes (27 <= nk <= 64) own all nk values of one element, so there is no shared
 // memory, no barrier and the input/output accesses are plain coalesced streams.  Same arithmetic and
 // reference lines as ktransform.cu (fftisdf.py:41-47, :79-85).  Input is [nk][rows][cols] with cols
 // contiguous; for the right-hand side the GEMM already produces the transposed fx^T[k][i][g], so the
@@ -133,27 +133,36 @@ __global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
   }
 }
 
-// Lane-split variant for 32 < nk <= 64 with one axis of length 4: four lanes share an element, each holding
-// the slab with split-axis index `sub`; the two local axes are transformed in registers, the split axis with
-// warp shuffles.  Lane = sub*8 + e, so the 8 elements of a warp stay contiguous in memory per slab.
+// Lane-split variant: NS = 3 or 4 lanes (the length of the split axis SA) share an element, each holding the
+// slab with split-axis index `sub`; the two local axes are transformed in registers, the split axis with warp
+// shuffles.  Lane = sub*E + e with E = 32/NS elements per warp (NS = 3 leaves two lanes idle), so the E elements
+// of a warp stay contiguous in memory per slab.  A third / quarter of the registers of the one-thread kernel,
+// i.e. 3-4x the resident warps and loads in flight: the stage is latency-bound, not flop-bound.
+template <int N1, int N2, int N3, int SA>
+struct KtSplit {
+  static constexpr int NS = (SA == 0) ? N1 : (SA == 1) ? N2 : N3;
+  static constexpr int E = 32 / NS;
+  static constexpr int NA = (SA == 0) ? N2 : N1;
+  static constexpr int NB = (SA == 2) ? N2 : N3;
+  static constexpr int NL = NA * NB;
+};
+
 template <int N1, int N2, int N3, int SA, bool CONJ>
-__device__ __forceinline__ void kt_split_transform(cplx (&x)[(N1 * N2 * N3) / 4], int sub, int lane) {
-  constexpr int NA = (SA == 0) ? N2 : N1;
-  constexpr int NB = (SA == 2) ? N2 : N3;
+__device__ __forceinline__ void kt_split_transform(cplx (&x)[KtSplit<N1, N2, N3, SA>::NL], int sub, int e) {
+  using T = KtSplit<N1, N2, N3, SA>;
+  constexpr int NA = T::NA, NB = T::NB, NL = T::NL, NS = T::NS, E = T::E;
   constexpr int AXA = (SA == 0) ? 1 : 0;
   constexpr int AXB = (SA == 2) ? 1 : 2;
-  constexpr int NL = NA * NB;
   dft_axis<NB, 1, NL, AXB, CONJ>(x);
   dft_axis<NA, NB, NL, AXA, CONJ>(x);
-  const int e = lane & 7;
 #pragma unroll
   for (int l = 0; l < NL; ++l) {
     cplx acc = make_double2(0.0, 0.0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NS; ++j) {
       cplx v;
-      v.x = __shfl_sync(0xffffffffu, x[l].x, j * 8 + e);
-      v.y = __shfl_sync(0xffffffffu, x[l].y, j * 8 + e);
+      v.x = __shfl_sync(0xffffffffu, x[l].x, j * E + e);
+      v.y = __shfl_sync(0xffffffffu, x[l].y, j * E + e);
       cplx u = c_uax[SA][sub][j];
       if (CONJ) u.y = -u.y;
       cfma(acc, u, v);
@@ -164,15 +173,15 @@ __device__ __forceinline__ void kt_split_transform(cplx (&x)[(N1 * N2 * N3) / 4]
 
 template <int N1, int N2, int N3, int SA>
 __global__ void __launch_bounds__(128) ktransform_split_kernel(KtRegParams p) {
-  static_assert(((SA == 0) ? N1 : (SA == 1) ? N2 : N3) == 4, "split axis must have length 4");
-  constexpr int NA = (SA == 0) ? N2 : N1;
-  constexpr int NB = (SA == 2) ? N2 : N3;
-  constexpr int NL = NA * NB;
+  using T = KtSplit<N1, N2, N3, SA>;
+  static_assert(T::NS == 3 || T::NS == 4, "split axis must have length 3 or 4");
+  constexpr int NB = T::NB, NL = T::NL, NS = T::NS, E = T::E;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane >> 3, e = lane & 7;
-  const int c = (blockIdx.x * 4 + warp) * 8 + e;
+  const bool lane_on = lane < NS * E;                 // NS = 3: lanes 30, 31 only take part in the shuffles
+  const int sub = lane_on ? lane / E : NS - 1, e = lane_on ? lane % E : E - 1;
+  const int c = (blockIdx.x * 4 + warp) * E + e;
   const int r = blockIdx.y;
-  const bool valid = c < p.ncols;
+  const bool valid = lane_on && c < p.ncols;
   auto kof = [&](int l) {
     const int a = l / NB, b = l % NB;
     return (SA == 0) ? ((sub * N2 + a) * N3 + b) : (SA == 1) ? ((a * N2 + sub) * N3 + b) : ((a * N2 + b) * N3 + sub);
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(128) ktransform_split_kernel(KtRegParams p) {
   const cplx* src = p.in + (long)r * p.in_sr + (valid ? c : 0);
 #pragma unroll
   for (int l = 0; l < NL; ++l) x[l] = valid ? src[(long)kof(l) * p.in_sk] : make_double2(0.0, 0.0);
-  kt_split_transform<N1, N2, N3, SA, false>(x, sub, lane);
+  kt_split_transform<N1, N2, N3, SA, false>(x, sub, e);
   double mx_im = 0.0, mx_re = 0.0;
 #pragma unroll
   for (int l = 0; l < NL; ++l) {
@@ -197,8 +206,8 @@ __global__ void __launch_bounds__(128) ktransform_split_kernel(KtRegParams p) {
     }
   }
   if (p.mode != 2) {
-    if (p.conj2) kt_split_transform<N1, N2, N3, SA, true>(x, sub, lane);
-    else kt_split_transform<N1, N2, N3, SA, false>(x, sub, lane);
+    if (p.conj2) kt_split_transform<N1, N2, N3, SA, true>(x, sub, e);
+    else kt_split_transform<N1, N2, N3, SA, false>(x, sub, e);
   }
   if (valid && p.mode != 2) {
 #pragma unroll
@@ -229,7 +238,8 @@ __global__ void __launch_bounds__(128) ktransform_split_kernel(KtRegParams p) {
 
 template <int N1, int N2, int N3, int SA>
 static cudaError_t launch_split(const KtRegParams& p, cudaStream_t st) {
-  dim3 grid((p.ncols + 31) / 32, p.nrows);
+  constexpr int CB = 4 * KtSplit<N1, N2, N3, SA>::E;   // columns per 4-warp block
+  dim3 grid((p.ncols + CB - 1) / CB, p.nrows);
   ktransform_split_kernel<N1, N2, N3, SA><<<grid, 128, 0, st>>>(p);
   return cudaGetLastError();
 }
@@ -275,7 +285,7 @@ extern "C" int isdf_ktransform_rows_ex(void* hv, const void* in, long in_sk, lon
   bool hit = false;
   KT_CASE(1, 1, 1) KT_CASE(1, 1, 2) KT_CASE(1, 2, 1) KT_CASE(2, 1, 1) KT_CASE(1, 2, 2) KT_CASE(2, 1, 2)
   KT_CASE(2, 2, 1) KT_CASE(2, 2, 2) KT_CASE(1, 1, 3) KT_CASE(1, 3, 1) KT_CASE(3, 1, 1) KT_CASE(1, 3, 3)
-  KT_CASE(3, 1, 3) KT_CASE(3, 3, 1) KT_CASE(3, 3, 3) KT_CASE(2, 2, 3) KT_CASE(2, 3, 2) KT_CASE(3, 2, 2)
+  KT_CASE(3, 1, 3) KT_CASE(3, 3, 1) KT_CASE(2, 2, 3) KT_CASE(2, 3, 2) KT_CASE(3, 2, 2)
   KT_CASE(2, 3, 3) KT_CASE(3, 2, 3) KT_CASE(3, 3, 2) KT_CASE(1, 2, 3) KT_CASE(1, 3, 2) KT_CASE(2, 1, 3)
   KT_CASE(2, 3, 1) KT_CASE(3, 1, 2) KT_CASE(3, 2, 1) KT_CASE(1, 1, 4) KT_CASE(1, 4, 1) KT_CASE(4, 1, 1)
   KT_CASE(2, 2, 4) KT_CASE(2, 4, 2) KT_CASE(4, 2, 2) KT_CASE(1, 4, 4) KT_CASE(4, 1, 4) KT_CASE(4, 4, 1)
@@ -283,7 +293,7 @@ extern "C" int isdf_ktransform_rows_ex(void* hv, const void* in, long in_sk, lon
 #define KT_SPLIT(a, b, c, sa) \
   if (n1 == a && n2 == b && n3 == c) { e = launch_split<a, b, c, sa>(p, st); hit = true; }
   KT_SPLIT(4, 4, 4, 0) KT_SPLIT(3, 4, 4, 1) KT_SPLIT(4, 3, 4, 0) KT_SPLIT(4, 4, 3, 0) KT_SPLIT(4, 3, 3, 0)
-  KT_SPLIT(3, 4, 3, 1) KT_SPLIT(3, 3, 4, 2)
+  KT_SPLIT(3, 4, 3, 1) KT_SPLIT(3, 3, 4, 2) KT_SPLIT(3, 3, 3, 0)
   if (!hit) return ISDF_ESIZE;
   ISDF_CUDA(h, e);
   return ISDF_OK;

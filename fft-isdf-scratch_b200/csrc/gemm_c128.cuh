@@ -215,8 +215,10 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN, REAL_ONLY), gemm_min_bloc
     if (!warp_live) continue;   // warp-uniform: this warp's block lies outside M x N (or above the diagonal)
     const cplx* tA = sA + (it % STAGES) * A_TILE;
     const cplx* tB = sB + (it % STAGES) * B_TILE;
+    const int kleft = K - (it % ktiles) * BK;   // a short last K tile (e.g. K = nao = 26) skips its all-zero steps
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
+      if (ks * 4 >= kleft) break;
       cplx a[MI], b[2];
 #pragma unroll
       for (int mi = 0; mi < MI; ++mi)
@@ -327,9 +329,13 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN, REAL_ONLY), gemm_min_bloc
 
 template <int BM_, int BN_, bool A_KSLOW, bool B_KSLOW, int MODE, bool REAL_ONLY, int EPI>
 inline cudaError_t launch_gemm(const GemmParams& p, int batch, cudaStream_t st) {
+  // 3M: the caller's aspect hint (BM_ < BN_: short and wide, e.g. the 64-row sweep blocks and their ragged tail)
+  // picks the transposed tile, so that a block row of <= 32 live rows keeps every warp busy.
   constexpr bool K3M = gemm_is_3m(REAL_ONLY);
-  constexpr int BM = K3M ? ISDF_GEMM_3M_BM : (ISDF_GEMM_SMALL ? 64 : BM_);
-  constexpr int BN = K3M ? ISDF_GEMM_3M_BN : (ISDF_GEMM_SMALL ? (REAL_ONLY ? 64 : ISDF_GEMM_4M_BN) : BN_);
+  constexpr bool WIDE = BM_ < BN_;
+  constexpr int BM = K3M ? (WIDE ? ISDF_GEMM_3M_BN : ISDF_GEMM_3M_BM) : (ISDF_GEMM_SMALL ? 64 : BM_);
+  constexpr int BN = K3M ? (WIDE ? ISDF_GEMM_3M_BM : ISDF_GEMM_3M_BN)
+                         : (ISDF_GEMM_SMALL ? (REAL_ONLY ? 64 : ISDF_GEMM_4M_BN) : BN_);
   using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW, gemm_bk(REAL_ONLY)>;
   auto kern = gemm_c128_kernel<BM, BN, A_KSLOW, B_KSLOW, MODE, REAL_ONLY, EPI>;
   static bool configured = false;

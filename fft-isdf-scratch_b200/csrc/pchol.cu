@@ -692,6 +692,13 @@ extern "C" int isdf_trsm_prepare(void* hv, const void* u, int ldu_rows, const in
   return ISDF_OK;
 }
 
+// One block row of a sweep: 64 x 32 tiles for full 64-row blocks, the transposed 32 x 64 tile for a ragged tail
+// of <= 32 live rows (every warp of the CTA then has live rows).
+static cudaError_t sweep_launch(const GemmParams& p, int batch, cudaStream_t st) {
+  if (p.M <= 32) return launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st);
+  return launch_gemm<128, 64, false, true, MODE_AB, false, EPI_STORE>(p, batch, st);
+}
+
 // In-place blocked substitution  T <- U^{-1} U^{-H} T  on T[batch][nP][ng] (row-major, ng contiguous).
 // Only the first nact rows (nact >= every batch member's rank) are touched: rows at and beyond the rank are
 // zero on input and stay zero, so neither their block rows nor their K range are executed.
@@ -717,7 +724,7 @@ extern "C" int isdf_trsm_sweeps(void* hv, const void* lfwd, const void* ubwd, vo
     p.C = (cplx*)t + (long)a * TB * ldt;
     p.M = (nact - a * TB < TB) ? (nact - a * TB) : TB;
     p.K = ((a + 1) * TB < nact) ? (a + 1) * TB : nact;
-    ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st)));
+    ISDF_CUDA(h, sweep_launch(p, batch, st));
   }
   for (int a = nblk - 1; a >= 0; --a) {  // backward: rows a..end
     p.A = (const cplx*)ubwd + (long)a * TB * nP + (long)a * TB;
@@ -725,7 +732,7 @@ extern "C" int isdf_trsm_sweeps(void* hv, const void* lfwd, const void* ubwd, vo
     p.C = (cplx*)t + (long)a * TB * ldt;
     p.M = (nact - a * TB < TB) ? (nact - a * TB) : TB;
     p.K = nact - a * TB;
-    ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st)));
+    ISDF_CUDA(h, sweep_launch(p, batch, st));
   }
   return ISDF_OK;
 }

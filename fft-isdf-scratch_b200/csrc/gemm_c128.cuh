@@ -230,19 +230,9 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN, REAL_ONLY), gemm_min_bloc
         // conj(a) b: (ar - ai)(br + bi);  a conj(b): (ar + ai)(br - bi);  a b: (ar + ai)(br + bi)
         double as[MI], bs[2];
 #pragma unroll
-        for (int mi = 0; mi < MI; ++mi)
-#ifdef ISDF_GEMM_DIAG_NOSUM   // timing diagnostic only (wrong results): how much do the DADDs cost?
-          as[mi] = a[mi].x;
-#else
-          as[mi] = (MODE == MODE_CONJA) ? a[mi].x - a[mi].y : a[mi].x + a[mi].y;
-#endif
+        for (int mi = 0; mi < MI; ++mi) as[mi] = (MODE == MODE_CONJA) ? a[mi].x - a[mi].y : a[mi].x + a[mi].y;
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
-#ifdef ISDF_GEMM_DIAG_NOSUM
-          bs[ni] = b[ni].y;
-#else
-          bs[ni] = (MODE == MODE_CONJB) ? b[ni].x - b[ni].y : b[ni].x + b[ni].y;
-#endif
+        for (int ni = 0; ni < 2; ++ni) bs[ni] = (MODE == MODE_CONJB) ? b[ni].x - b[ni].y : b[ni].x + b[ni].y;
 #pragma unroll
         for (int ni = 0; ni < 2; ++ni)
 #pragma unroll

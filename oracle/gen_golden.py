@@ -160,6 +160,14 @@ CASES = {
     # numerically full-rank A_q and exact time-reversal symmetry W_{-q} = W_q^*
     "k231_odd": dict(mesh=[9, 11, 7], nao=8, seed=14, kmesh=[2, 3, 1], m0=[6, 7, 5], c0=3.0, ltypes="spd", blksize=500,
                      skew=True),
+    # the headline k-mesh (3x3x3: lane-split register k-transform, 13 time-reversal pairs) and a 48-point mesh with
+    # two axes of length 4 (four-lane split), both on odd FFT meshes with full-rank, well-conditioned A_q
+    # (cond ~ 2e4; seeds 15/16 or c0 = 3 give cond(A_q) ~ 1e9-1e12 on these coarse parent grids, where the
+    # reference's own zgelsy output only reproduces to ~1e-8)
+    "k333_odd": dict(mesh=[7, 7, 9], nao=8, seed=17, kmesh=[3, 3, 3], m0=[5, 5, 5], c0=2.5, ltypes="spd", blksize=200,
+                     skew=True),
+    "k434_odd": dict(mesh=[5, 7, 5], nao=8, seed=17, kmesh=[4, 3, 4], m0=[4, 5, 4], c0=2.5, ltypes="spd", blksize=8000,
+                     skew=True),
 }
 
 
@@ -230,8 +238,10 @@ def _time_reversal(kmesh):
 
 def main():
     ref = load_reference()
+    only = sys.argv[1:]          # optional case names; default: regenerate every fixture
     for name, spec in CASES.items():
-        run_case(ref, name, spec)
+        if not only or name in only:
+            run_case(ref, name, spec)
 
 
 if __name__ == "__main__":

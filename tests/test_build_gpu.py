@@ -41,6 +41,7 @@ def run_golden(name, **attrs):
 
 
 @pytest.mark.parametrize("name,tol_w,tol_jk", [("k321_spd", 1e-10, 1e-10), ("k231_odd", 1e-10, 1e-10),
+                                               ("k333_odd", 1e-10, 1e-10), ("k434_odd", 1e-10, 1e-10),
                                                ("gamma_s", 1e-8, 1e-10)])
 def test_full_rank_cases_match_reference(name, tol_w, tol_jk):
     g, df = run_golden(name, keep_theta=True)
@@ -193,7 +194,7 @@ def test_eri_reconstruction_against_exact_pair_densities():
     assert worst < 1e-4, worst
 
 
-@pytest.mark.parametrize("name", ["k321_spd", "k231_odd", "gamma_s"])
+@pytest.mark.parametrize("name", ["k321_spd", "k231_odd", "k333_odd", "k434_odd", "gamma_s"])
 def test_device_jk_equals_host_jk_and_reference(name):
     """get_j_kpts / get_k_kpts on the device == the numpy statement of fftisdf.py:133-228 == golden."""
     g, df = run_golden(name)

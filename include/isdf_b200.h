@@ -12,8 +12,20 @@
  *     interleaved (re, im) doubles exactly as numpy / torch store it; matrices are row-major.
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
  *   - one handle per (process, device); a handle is not thread-safe.  The handle owns only small
- *     plans (FFT twiddle tables).
+ *     plans (FFT twiddle tables, DFT matrices) and a grow-only scratch for split-K partial sums.
  *   - there is no CPU path: isdf_create fails on anything that is not compute capability 10.x.
+ *
+ * Stage map (SURVEY.md section 8b names the stages of the path; each is this sequence of entry points,
+ * orchestrated by fft-isdf-scratch_b200/fftisdf.py:build, which also owns the multi-GPU exchanges):
+ *   select points   fftisdf.py:357-388  isdf_select_gram -> isdf_pchol_real -> isdf_gather_rows
+ *   build metric    fftisdf.py:38-48    isdf_gram_conja -> isdf_ktransform_square_rows (registers; k-mesh axes <= 4)
+ *                                       or isdf_ktransform_square (shared memory; axes <= 8)
+ *   build rhs       fftisdf.py:72-87    isdf_gram_conjb -> isdf_ktransform_square_rows, per grid block, rows written
+ *                                       straight into pivot order
+ *   fit theta       fftisdf.py:108      isdf_pchol -> isdf_trsm_prepare -> isdf_trsm_sweeps
+ *   coulomb kernel  fftisdf.py:96-122   isdf_phase_table + isdf_coulomb_weights -> isdf_dft3d_dmma (axes <= 48; _p2p
+ *                                       across GPUs) or isdf_fft3d_batched -> isdf_herk_scatter -> isdf_conj_copy
+ *   J / K           fftisdf.py:133-228  isdf_gemm_hn, isdf_rowdot_conj_sum, isdf_scale_rows, isdf_ktransform_rows_ex
  */
 #ifndef ISDF_B200_H
 #define ISDF_B200_H

@@ -309,9 +309,7 @@ def build(df_obj):
         # fused exchange: each rank transforms its nipP/world vectors of every q, reading the planes from and
         # writing the result to the ranks' column shards over NVLink inside the DFT kernels
         # (rows at positions >= max rank are identically zero: only the live rows are dealt out)
-        nv = -(-rmax // world)
-        v_lo = rank * nv
-        v_cnt = max(0, min(nv, rmax - v_lo))
+        v_lo, v_cnt = sharding.vector_shard(rmax, world, rank)
         work = torch.empty((max(v_cnt, 1), ngrid), dtype=torch.complex128, device=dev)
         peerbuf.barrier()                                    # every rank's Theta shard is complete
         for s, q in enumerate(qind):                                              # :97

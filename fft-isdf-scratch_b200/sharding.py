@@ -31,6 +31,14 @@ def col_shard(ng, world, rank):
     return lo, hi, c
 
 
+def vector_shard(nlive, world, rank):
+    """Contiguous shard of the live interpolation vectors (rows below the maximum rank) for the FFT stage:
+    returns (lo, count); the counts of all ranks add up to nlive, trailing ranks may get none."""
+    per = -(-nlive // world)
+    lo = rank * per
+    return lo, max(0, min(per, nlive - lo))
+
+
 def slot_shard(nslot, world, rank):
     """Round-robin assignment of q-slots to ranks (factorisation of A_q)."""
     return list(range(rank, nslot, world))

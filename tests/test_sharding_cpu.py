@@ -62,6 +62,18 @@ def test_layouts_world2_gloo(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
+def test_vector_shard_covers_live_rows_once():
+    from fft_isdf_scratch_b200 import sharding as S
+    for nlive in (0, 1, 7, 52, 413, 2140):
+        for w in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(w):
+                lo, cnt = S.vector_shard(nlive, w, r)
+                assert cnt >= 0 and (cnt == 0 or lo + cnt <= nlive)
+                seen += list(range(lo, lo + cnt))
+            assert seen == list(range(nlive))
+
+
 def test_col_shard_covers_grid():
     from fft_isdf_scratch_b200 import sharding as S
     for ng in (1, 7, 50653, 32768):

@@ -31,3 +31,16 @@ def test_flop_model_matches_oracle_model():
     a = bench.flop_model(27, 26, 3375, 520, 50653)
     b = O.flop_model(27, 26, 3375, 520, 50653)
     assert a == b and 9.0e12 < a["total"] < 1.0e13      # cfg2 ~ 9.5e12
+
+
+def test_sweep_mac_count_matches_the_launch_schedule():
+    """roofline.achieved counts the MACs of the sweep launches: for a full-rank multiple of 64 that is r(r+64) per
+    column (two triangular solves with 64-blocks), and a ragged tail only adds what it uses."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.sweep_macs_per_column(448) == 448 * (448 + 64)
+    assert bench.sweep_macs_per_column(64) == 2 * 64 * 64
+    r = 413
+    dense = sum(min(64 * (i // 64 + 1), r) for i in range(r)) + sum(r - 64 * (i // 64) for i in range(r))
+    assert bench.sweep_macs_per_column(r) == dense
+    assert bench.sweep_macs_per_column(413) < bench.sweep_macs_per_column(448) * 0.87

@@ -184,6 +184,7 @@ extern "C" int isdf_herk_scatter(void* hv, const void* b, long ldb, long strideB
   cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, b && w, "null pointer");
   ISDF_CHECK_ARG(h, n >= 0 && k >= 0 && batch >= 0 && batch <= 65535, "shape");
+  if (n == 0 || batch == 0) return ISDF_OK;   // nothing to write (e.g. every rank is zero)
   GemmParams p;
   p.A = (const cplx*)b; p.lda = ldb; p.strideA = strideB;
   p.B = (const cplx*)b; p.ldb = ldb; p.strideB = strideB;

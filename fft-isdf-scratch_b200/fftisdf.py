@@ -29,6 +29,7 @@ import numpy
 import torch
 
 from . import pbc_tools, sharding
+from .eri_transform import KPT_DIFF_TOL, trans_2e  # noqa: F401  (the stub at fftisdf.py:230-294, completed)
 from .kernels import IsdfOps, TB
 
 try:  # pragma: no cover - PySCF is not in the build image

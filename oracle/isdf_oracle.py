@@ -166,6 +166,26 @@ def eri_from_w(wq_q, x1, x2, x3, x4):
     return numpy.einsum("IJ,Imn,Jkl->mnkl", wq_q, l, r, optimize=True)
 
 
+def trans_2e_bruteforce(x, wq, kmesh, c_ao_emb):
+    """Definition-level statement of the embedding ERI the stub at fftisdf.py:230-294 sets up (it stops before the
+    contraction): sum over the momentum-conserving quadruples of eri_from_w with xmo = C_ao_emb[k].T @ x[k].T (:287).
+    c_ao_emb [nk, nao, nemb] (already carrying the nkpts**-0.75 factor, :275-276).  Test oracle only."""
+    import itertools
+    nk = len(x)
+    kidx = numpy.array(list(itertools.product(*[range(n) for n in kmesh])))
+    find = lambda v: int(numpy.where((kidx == numpy.mod(v, kmesh)).all(1))[0][0])
+    xe = [x[k] @ c_ao_emb[k] for k in range(nk)]                  # [nip, nemb] = (C^T x^T)^T
+    nemb = c_ao_emb.shape[-1]
+    eri = numpy.zeros((nemb,) * 4, dtype=numpy.complex128)
+    for k1 in range(nk):
+        for k2 in range(nk):
+            q = find(kidx[k2] - kidx[k1])
+            for k3 in range(nk):
+                k4 = find(kidx[k3] - kidx[q])
+                eri += eri_from_w(wq[q], xe[k1], xe[k2], xe[k3], xe[k4])
+    return eri
+
+
 def flop_model(nk, nao, n0, nip, ng, nq=None):
     """SURVEY.md section 8(d) / BASELINE.md section 3 algorithmic work (real flop; complex MAC = 8)."""
     import math

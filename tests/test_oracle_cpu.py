@@ -158,3 +158,72 @@ def test_time_reversal_rule_odd_mesh():
     cg = [T.get_coulG(a, k, [8, 9, 10]) for k in kp]
     ok = _time_reversal_valid([3, 2, 1], [8, 9, 10], cg, T.time_reversal_partner([3, 2, 1]))
     assert not ok.any()
+
+
+def _exact_isdf_factors(side, kmesh, nao=2, seed=81):
+    """Tiny cell in the exact-ISDF regime (every grid point a candidate, nip = full rank), built by the oracle."""
+    import types
+    import fft_isdf_scratch_b200 as pk
+    cell = pk.random_cubic_cell(side, nao, seed=seed, L=5.0, ltypes="s")
+    kpts = cell.get_kpts(kmesh)
+    coord = cell.gen_uniform_grids(cell.mesh)
+    phi = cell.eval_ao_kpts(coord, kpts)
+    out = O.build(cell.a, kpts, kmesh, list(cell.mesh), phi, phi, coord, 50.0)
+    return cell, types.SimpleNamespace(_x=out["x"], _wq=out["wq"], kmesh=kmesh, kpts=kpts, cell=cell)
+
+
+@pytest.mark.parametrize("side,kmesh", [(6, [2, 1, 1]), (6, [2, 2, 1]), (5, [3, 1, 1])])
+def test_trans_2e_default_is_the_supercell_eri(side, kmesh):
+    """with C_ao_lo = C_lo_eo = identity ("k2gamma AO transformation", fftisdf.py:246) the embedding
+    ERIs are the ERIs of the supercell AOs.  Pins the R->k phase e^{-ik.R}, the nkpts**-0.75 normalisation (:275) and
+    the momentum convention against EXPLICIT supercell pair densities (exact-ISDF regime, so no fitting error)."""
+    import fft_isdf_scratch_b200 as pk
+    from fft_isdf_scratch_b200 import eri_transform as E
+    cell, df = _exact_isdf_factors(side, kmesh)
+    eri = E.trans_2e(df)[0]
+    rvec = pk.pbc_tools.translation_vectors_for_kmesh(cell.a, kmesh)
+    shells = [(cell._cen[i], "s", cell._alp[i]) for i in range(cell.nao_nr())]
+    mesh_sc = [int(m * k) for m, k in zip(cell.mesh, kmesh)]
+    sup = pk.SyntheticCell(np.diag(kmesh) @ cell.a, [(c + r, l, al) for r in rvec for (c, l, al) in shells], mesh_sc)
+    csc = sup.gen_uniform_grids(mesh_sc)
+    chi = sup.eval_ao_kpts(csc, np.zeros((1, 3)))[0].real
+    n, ng = chi.shape[1], len(csc)
+    rho = np.einsum("gm,gn->mng", chi, chi).reshape(n * n, ng)
+    zeta = H.ifft(H.fft(rho, mesh_sc) * H.get_coulG(sup.a, np.zeros(3), mesh_sc) * sup.vol / ng, mesh_sc)
+    ref = (zeta @ rho.T).reshape(n, n, n, n)
+    assert np.abs(eri - ref).max() < 1e-10 * np.abs(ref).max()
+    assert np.abs(eri.imag).max() < 1e-12 * np.abs(ref).max()
+    packed = E.trans_2e(df, symmetry=4)[0]
+    tri = np.tril_indices(n)
+    assert np.abs(packed - ref[tri[0], tri[1]][:, tri[0], tri[1]]).max() < 1e-10 * np.abs(ref).max()
+
+
+def test_trans_2e_matches_definition_for_general_orbitals():
+    """Random k-space C_ao_lo, R-space C_lo_eo, two spins: the factored contraction == the quadruple sum."""
+    from fft_isdf_scratch_b200 import eri_transform as E
+    import types
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_k231_odd.npz"))
+    kmesh = g["kmesh"].tolist()
+    nk, nip, nao = g["x"].shape
+    cell = types.SimpleNamespace(lattice_vectors=lambda: g["a"])
+    df = types.SimpleNamespace(_x=g["x"], _wq=g["wq"], kmesh=kmesh, kpts=g["kpts"], cell=cell)
+    rng = np.random.default_rng(5)
+    nlo, nemb = 5, 3
+    c_ao_lo = rng.standard_normal((2, nk, nao, nlo)) + 1j * rng.standard_normal((2, nk, nao, nlo))
+    c_lo_eo = rng.standard_normal((1, nk, nlo, nemb))
+    eri = E.trans_2e(df, C_ao_lo=c_ao_lo, C_lo_eo=c_lo_eo)
+    assert eri.shape == (3, nemb, nemb, nemb, nemb)
+    import itertools
+    rvec = np.array(list(itertools.product(*[range(n) for n in kmesh]))) @ g["a"]
+    ph = np.exp(-1j * rvec @ g["kpts"].T)
+    c_emb = [np.einsum("kal,kln->kan", c_ao_lo[s], np.einsum("Rk,Rln->kln", ph, c_lo_eo[0])) / nk ** 0.75 for s in range(2)]
+    ref_aa = O.trans_2e_bruteforce(g["x"], g["wq"], kmesh, c_emb[0])
+    assert np.abs(eri[0] - ref_aa).max() < 1e-12 * np.abs(ref_aa).max()
+    ref_bb = O.trans_2e_bruteforce(g["x"], g["wq"], kmesh, c_emb[1])
+    assert np.abs(eri[1] - ref_bb).max() < 1e-12 * np.abs(ref_bb).max()
+    # unit_eri: C_ao_emb = C_ao_lo / nk^{3/4} (fftisdf.py:275-276)
+    eri_u = E.trans_2e(df, C_ao_lo=c_ao_lo[0], unit_eri=True)
+    ref_u = O.trans_2e_bruteforce(g["x"], g["wq"], kmesh, c_ao_lo[0] / nk ** 0.75)
+    assert eri_u.shape == (1, nlo, nlo, nlo, nlo) and np.abs(eri_u[0] - ref_u).max() < 1e-12 * np.abs(ref_u).max()
+    with pytest.raises(NotImplementedError):
+        E.trans_2e(df, kscaled_center=[0.5, 0.0, 0.0])

@@ -48,6 +48,18 @@ SIGNATURES = {
                    c_void_p, c_void_p, c_void_p],
     "isdf_pchol_real": [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_int, c_void_p, c_void_p,
                         c_void_p, c_void_p, c_void_p],
+    "isdf_chol_nopivot": [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                          c_void_p, c_void_p],
+    "isdf_trsm_sweep": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_long, c_int, c_int, c_void_p],
+    "isdf_qrcp": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "isdf_gelsy_rank": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p],
+    "isdf_gelsy_extract": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                           c_void_p, c_void_p, c_void_p, c_void_p],
+    "isdf_gelsy_rhat": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "isdf_gelsy_q1_finish": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "isdf_hermitize": [c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "isdf_gemm_tn": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_long, c_long,
+                     c_int, c_int, c_int, c_int, c_void_p],
     "isdf_trsm_prepare": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                           c_void_p, c_void_p],
     "isdf_trsm_sweeps": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_long, c_int, c_void_p],

@@ -46,7 +46,8 @@ __global__ void pchol_init_kernel(int* pos, PcholInfo* info, int* active, int n,
 
 __global__ void __launch_bounds__(PC_THREADS, 1)
 pchol_panel_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n, int j0, int nb, int max_steps,
-                   double tol, cplx* Uall, long ldu, long strideU, int* posall, PcholInfo* infoall, int* active) {
+                   double tol, cplx* Uall, long ldu, long strideU, int* posall, PcholInfo* infoall, int* active,
+                   int nopivot) {
   const int b = blockIdx.x;
   PcholInfo* info = infoall + b;
   if (info->done) return;
@@ -88,7 +89,7 @@ pchol_panel_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n,
     int bpos = 0x7fffffff, bidx = -1;
 #pragma unroll
     for (int c = 0; c < PC_NCOL; ++c) {
-      if (mypos[c] >= j) {
+      if (nopivot ? (mypos[c] == j) : (mypos[c] >= j)) {
         const double d = s_aii[tid + c * PC_THREADS] - ssum[c];
         if (d > bv || (d == bv && mypos[c] < bpos)) { bv = d; bpos = mypos[c]; bidx = tid + c * PC_THREADS; }
       }
@@ -218,7 +219,7 @@ template <bool REALP>
 __global__ void __cluster_dims__(PCC_CS, 1, 1) __launch_bounds__(PCC_THREADS, 1)
 pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA, int n, int ncc, int j0, int nb,
                            int max_steps, double tol, cplx* Uall, long ldu, long strideU, int* posall,
-                           PcholInfo* infoall, int* active) {
+                           PcholInfo* infoall, int* active, int nopivot) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int b = blockIdx.y;
@@ -269,7 +270,7 @@ pchol_panel_cluster_kernel(const cplx* __restrict__ Aall, long lda, long strideA
     int bpos = 0x7fffffff, bidx = -1;
 #pragma unroll
     for (int c = 0; c < PCC_NCOL; ++c) {
-      if (mypos[c] >= j) {
+      if (nopivot ? (mypos[c] == j) : (mypos[c] >= j)) {
         const int lc = tid + c * PCC_THREADS;
         const double d = s_aii[lc] - ssum[c];
         if (d > bv || (d == bv && mypos[c] < bpos)) { bv = d; bpos = mypos[c]; bidx = c_lo + lc; }
@@ -567,7 +568,8 @@ extern "C" int isdf_pchol_workspace_bytes(int n, int batch, size_t* bytes) {
 // u: [batch][ldu_rows][n] c128, rows j < rank hold row j of the factor A = U^H U in ORIGINAL column
 //    order (column piv[j] carries the pivot); must be zero-initialised by the caller? -> zeroed here.
 static int pchol_run(Handle* h, void* a, int n, int batch, int max_steps, double tol, int nb, void* u, int ldu_rows,
-                     int* piv, int* rank, double* next_pivot, void* workspace, void* stream, bool is_real);
+                     int* piv, int* rank, double* next_pivot, void* workspace, void* stream, bool is_real,
+                     int nopivot = 0);
 
 extern "C" int isdf_pchol(void* hv, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
                           int ldu_rows, int* piv, int* rank, double* next_pivot, void* workspace, void* stream) {
@@ -583,8 +585,18 @@ extern "C" int isdf_pchol_real(void* hv, void* a, int n, int batch, int max_step
                    true);
 }
 
+// Unpivoted Cholesky A = U^H U through the same kernels (pivot = next position): used by the Cholesky-QR that
+// orthonormalises the rows of the scaled [R11 R12] factor of the gelsy fit (fftisdf.py:108).  Stops at the first
+// pivot <= tol (tol = 0: an exactly singular trailing block).
+extern "C" int isdf_chol_nopivot(void* hv, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
+                                 int ldu_rows, int* piv, int* rank, void* workspace, void* stream) {
+  return pchol_run((Handle*)hv, a, n, batch, max_steps, tol, nb, u, ldu_rows, piv, rank, nullptr, workspace, stream,
+                   false, 1);
+}
+
 static int pchol_run(Handle* h, void* a, int n, int batch, int max_steps, double tol, int nb, void* u, int ldu_rows,
-                     int* piv, int* rank, double* next_pivot, void* workspace, void* stream, bool is_real) {
+                     int* piv, int* rank, double* next_pivot, void* workspace, void* stream, bool is_real,
+                     int nopivot) {
   cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, a && u && piv && rank && workspace, "null pointer");
   ISDF_CHECK_ARG(h, n >= 1 && n <= PC_THREADS * PC_NCOL, "n must be in [1, 8192]");
@@ -628,13 +640,15 @@ static int pchol_run(Handle* h, void* a, int n, int batch, int max_steps, double
     if (use_cluster) {
       if (is_real)
         pchol_panel_cluster_kernel<true><<<dim3(PCC_CS, batch), PCC_THREADS, csmem, st>>>(
-            (const cplx*)a, n, strideA, n, ncc, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);
+            (const cplx*)a, n, strideA, n, ncc, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active,
+            nopivot);
       else
         pchol_panel_cluster_kernel<false><<<dim3(PCC_CS, batch), PCC_THREADS, csmem, st>>>(
-            (const cplx*)a, n, strideA, n, ncc, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);
+            (const cplx*)a, n, strideA, n, ncc, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active,
+            nopivot);
     } else {
       pchol_panel_kernel<<<batch, PC_THREADS, (size_t)n * sizeof(double), st>>>(
-          (const cplx*)a, n, strideA, n, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active);
+          (const cplx*)a, n, strideA, n, j0, nb, max_steps, tol, (cplx*)u, n, strideU, pos, info, active, nopivot);
     }
     ISDF_LAUNCH_CHECK(h);
     if (j0 + nb < max_steps) {
@@ -697,6 +711,45 @@ extern "C" int isdf_trsm_prepare(void* hv, const void* u, int ldu_rows, const in
 static cudaError_t sweep_launch(const GemmParams& p, int batch, cudaStream_t st) {
   if (p.M <= 32) return launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st);
   return launch_gemm<128, 64, false, true, MODE_AB, false, EPI_STORE>(p, batch, st);
+}
+
+// One direction only: backward = 0: T <- U^{-H} T with op = lfwd;  backward = 1: T <- U^{-1} T with op = ubwd.
+extern "C" int isdf_trsm_sweep(void* hv, const void* op, void* t, int nP, int nact, long ng, long ldt, int batch,
+                               int backward, void* stream) {
+  Handle* h = (Handle*)hv;
+  cudaStream_t st = (cudaStream_t)stream;
+  ISDF_CHECK_ARG(h, op && t, "null pointer");
+  ISDF_CHECK_ARG(h, nP % TB == 0 && ng >= 1 && ng < (1L << 31) && ldt >= ng, "shape");
+  ISDF_CHECK_ARG(h, nact >= 0 && nact <= nP, "nact out of range");
+  if (nact == 0) return ISDF_OK;
+  const int nblk = (nact + TB - 1) / TB;
+  GemmParams p;
+  p.lda = nP; p.strideA = (long)nP * nP;
+  p.ldb = ldt; p.strideB = (long)nP * ldt;
+  p.ldc = ldt; p.strideC = (long)nP * ldt;
+  p.N = (int)ng;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
+  if (!backward) {
+    for (int a = 0; a < nblk; ++a) {
+      p.A = (const cplx*)op + (long)a * TB * nP;
+      p.B = (const cplx*)t;
+      p.C = (cplx*)t + (long)a * TB * ldt;
+      p.M = (nact - a * TB < TB) ? (nact - a * TB) : TB;
+      p.K = ((a + 1) * TB < nact) ? (a + 1) * TB : nact;
+      ISDF_CUDA(h, sweep_launch(p, batch, st));
+    }
+  } else {
+    for (int a = nblk - 1; a >= 0; --a) {
+      p.A = (const cplx*)op + (long)a * TB * nP + (long)a * TB;
+      p.B = (const cplx*)t + (long)a * TB * ldt;
+      p.C = (cplx*)t + (long)a * TB * ldt;
+      p.M = (nact - a * TB < TB) ? (nact - a * TB) : TB;
+      p.K = nact - a * TB;
+      ISDF_CUDA(h, sweep_launch(p, batch, st));
+    }
+  }
+  return ISDF_OK;
 }
 
 // In-place blocked substitution  T <- U^{-1} U^{-H} T  on T[batch][nP][ng] (row-major, ng contiguous).

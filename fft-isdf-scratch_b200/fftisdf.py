@@ -16,8 +16,9 @@ Deliberate differences from the reference, all documented in DESIGN.md:
   * `kpts = self.cell.get_kpts(kmesh)` uses self.cell (the reference reads a module global, :322).
   * W_q is formed in G space, W_q = B B^H with B = FFT[Theta_q e^{-iq.r}] sqrt(v(q+G) vol)/ng, which is
     algebraically identical to :113-121 (Parseval) and Hermitian by construction.
-  * A_q Theta_q = Y_q^T is solved by a rank-revealing (diagonally pivoted) Cholesky factorisation
-    instead of LAPACK zgelsy; identical to rounding when A_q is numerically full rank.
+  * A_q Theta_q = Y_q^T is solved with LAPACK zgelsy's algorithm restated on the device (QRCP, rank by
+    incremental condition estimation with rcond = eps, complete orthogonal factorisation); `fit = "cholesky"`
+    selects the cheaper rank-revealing Cholesky route (identical to rounding only when A_q has full rank).
   * only one of each time-reversal pair (q, -q) is computed; the partner is the complex conjugate.
   * additive attributes: `_mask` (interpolation-point indices), `_ranks`, `_theta` (optional).
 """
@@ -195,43 +196,77 @@ def build(df_obj):
     if getattr(df_obj, "keep_metric", False):
         df_obj._a_q = a_q.clone()
 
-    # ---- C(a). rank-revealing Cholesky of every A_q (replaces the QRCP inside zgelsy, :108);
-    #      q-slots are dealt round-robin to the ranks and the factors all-gathered.
+    # ---- C(a). factorisation of every A_q; q-slots are dealt round-robin to the ranks and the operators all-gathered.
+    #   fit = "gelsy" (default, the reference's solver, :108): LAPACK zgelsy restated on the device -- Householder QRCP,
+    #         rank by incremental condition estimation with rcond = eps, complete orthogonal factorisation -- kept as
+    #         three dense operators per q (kernels.py:gelsy_operators).
+    #   fit = "cholesky": rank-revealing (diagonally pivoted) Cholesky, basic solution on the kept points; identical to
+    #         gelsy to rounding when A_q has full numerical rank, cheaper, but NOT the reference's truncation otherwise.
+    fit = getattr(df_obj, "fit", "gelsy")
+    assert fit in ("gelsy", "cholesky")
     rcond = getattr(df_obj, "rcond", -1.0)
     mine = sharding.slot_shard(nq, world, rank)
-    if mine:
-        a_mine = a_q[mine].contiguous() if world > 1 else a_q
-        u_q, piv_l, rank_l, _ = ops.pchol(a_mine, max_steps=nip, tol=rcond, nb=df_obj.chol_nb)
-        del a_mine
-    else:
-        u_q = None
-        piv_l = torch.zeros((0, nip), dtype=torch.int32, device=dev)
-        rank_l = torch.zeros((0,), dtype=torch.int32, device=dev)
+    a_mine = (a_q[mine].contiguous() if world > 1 else a_q) if mine else None
     del a_q
-    piv_q = sharding.allgather_slots(piv_l, nq, comm)
+    if fit == "gelsy":
+        if mine:
+            qr_state = ops.gelsy_qr(a_mine, rcond if rcond > 0 else float(numpy.finfo(numpy.float64).eps))
+            rank_l = qr_state["rank"]
+        else:
+            qr_state = None
+            rank_l = torch.zeros((0,), dtype=torch.int32, device=dev)
+        piv_q = None
+    else:
+        if mine:
+            u_q, piv_l, rank_l, _ = ops.pchol(a_mine, max_steps=nip, tol=rcond, nb=df_obj.chol_nb)
+        else:
+            u_q = None
+            piv_l = torch.zeros((0, nip), dtype=torch.int32, device=dev)
+            rank_l = torch.zeros((0,), dtype=torch.int32, device=dev)
+        piv_q = sharding.allgather_slots(piv_l, nq, comm)
+    del a_mine
     rank_q = sharding.allgather_slots(rank_l, nq, comm)
-    piv_h = piv_q.cpu().numpy()
     rank_h = rank_q.cpu().numpy()
-    stats["d2h_bytes"] += piv_h.nbytes + rank_h.nbytes
+    stats["d2h_bytes"] += rank_h.nbytes
+    assert rank_h.min() >= 1, "a metric A_q is identically zero"
     # rows at positions >= max rank are identically zero from here on: drop them (multiple of 64 and of world)
     nipP = max(TB, -(-int(rank_h.max()) // TB) * TB)
     while nipP % world:
         nipP += TB
-    if mine:
-        lf_l, ub_l = ops.trsm_prepare(u_q, piv_l, rank_l, nipP)
+    if fit == "gelsy":
+        if mine:
+            fac = ops.gelsy_operators(qr_state, nipP)
+            q1_l, lf_l, eh_l = fac["q1s"], fac["lfwd"], fac["eh"]
+            del fac
+        else:
+            q1_l = torch.zeros((0, nip, nipP), dtype=torch.complex128, device=dev)
+            lf_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
+            eh_l = torch.zeros((0, nipP, nip), dtype=torch.complex128, device=dev)
+        del qr_state
+        q1s = sharding.AsyncSlotGather(q1_l, nq, comm).result()     # needed by the first grid block
+        lfwd_g = sharding.AsyncSlotGather(lf_l, nq, comm)
+        ehg = sharding.AsyncSlotGather(eh_l, nq, comm)
+        ubwd_g = None
+        del q1_l, lf_l, eh_l
+        rowmap = None
     else:
-        lf_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
-        ub_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
-    del u_q
-    # the (large) all-gather of the sweep operators runs on NCCL's stream while the right-hand side is built
-    lfwd_g = sharding.AsyncSlotGather(lf_l, nq, comm)
-    ubwd_g = sharding.AsyncSlotGather(ub_l, nq, comm)
-    del lf_l, ub_l
-    rowmap_h = -numpy.ones((nq, nip), dtype=numpy.int32)
-    for s in range(nq):
-        r = int(rank_h[s])
-        rowmap_h[s, piv_h[s, :r]] = numpy.arange(r, dtype=numpy.int32)
-    rowmap = torch.from_numpy(rowmap_h).to(dev)
+        piv_h = piv_q.cpu().numpy()
+        stats["d2h_bytes"] += piv_h.nbytes
+        if mine:
+            lf_l, ub_l = ops.trsm_prepare(u_q, piv_l, rank_l, nipP)
+        else:
+            lf_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
+            ub_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
+        del u_q
+        # the (large) all-gather of the sweep operators runs on NCCL's stream while the right-hand side is built
+        lfwd_g = sharding.AsyncSlotGather(lf_l, nq, comm)
+        ubwd_g = sharding.AsyncSlotGather(ub_l, nq, comm)
+        del lf_l, ub_l
+        rowmap_h = -numpy.ones((nq, nip), dtype=numpy.int32)
+        for s in range(nq):
+            r = int(rank_h[s])
+            rowmap_h[s, piv_h[s, :r]] = numpy.arange(r, dtype=numpy.int32)
+        rowmap = torch.from_numpy(rowmap_h).to(dev)
     mark("metric")
 
     # ---- B2. right-hand side Y_q^T for this rank's grid columns, written straight into pivot order  :72-87
@@ -252,6 +287,7 @@ def build(df_obj):
         theta = torch.zeros((nq, nipP, ncol), dtype=torch.complex128, device=dev)
     blksize = int(df_obj.blksize)
     fx_k = None
+    y_blk = None        # gelsy: Y^T of one grid block [nq, nip, blk] (natural row order), projected by Q1^H at once
     if upload_done is not None:
         torch.cuda.current_stream().wait_event(upload_done)
     for ao_k_etc, g0, g1 in df_obj.aoR_loop(grids, vk, 0, blksize=blksize, g_range=(g_lo, g_hi)):   # :72
@@ -268,35 +304,66 @@ def build(df_obj):
             sub = max(64, min(blk, int(df_obj.rhs_l2_bytes // (nkpt * nip * 16)) // 64 * 64))
             if fx_k is None or fx_k.numel() != nkpt * sub * nip:
                 fx_k = torch.empty((nkpt * sub * nip,), dtype=torch.complex128, device=dev)
+            if fit == "gelsy" and (y_blk is None or y_blk.numel() != nq * nip * sub):
+                y_blk = torch.empty((nq * nip * sub,), dtype=torch.complex128, device=dev)
             for s0 in range(0, blk, sub):
                 sb = min(sub, blk - s0)
                 fxt = fx_k[: nkpt * nip * sb].view(nkpt, nip, sb)
                 ops.gram_conjb(xip, f_k[:, s0:s0 + sb, :], out=fxt)
-                ops.ktransform_rows(fxt, nip * sb, sb, theta, nipP * ncol, ncol, g0 - g_lo + s0, nip, sb, kmesh, uax_h,
-                                    conj2=0, qslot=qslot, rowmap=rowmap, rowmap_sq=nip, diag=diag[2:4])   # :79-85
+                if fit == "gelsy":
+                    yv = y_blk[: nq * nip * sb].view(nq, nip, sb)
+                    ops.ktransform_rows(fxt, nip * sb, sb, yv, nip * sb, sb, 0, nip, sb, kmesh, uax_h,
+                                        conj2=0, qslot=qslot, diag=diag[2:4])                               # :79-85
+                    c0 = g0 - g_lo + s0
+                    ops.gemm_hn_strided(q1s, yv, theta[:, :, c0:c0 + sb])     # (Q1 D^-1)^H Y^T  (zunmqr of zgelsy, :108)
+                else:
+                    ops.ktransform_rows(fxt, nip * sb, sb, theta, nipP * ncol, ncol, g0 - g_lo + s0, nip, sb, kmesh,
+                                        uax_h, conj2=0, qslot=qslot, rowmap=rowmap, rowmap_sq=nip, diag=diag[2:4])   # :79-85
         else:
             if fx_k is None or fx_k.numel() != nkpt * blk * nip:
                 fx_k = torch.empty((nkpt * blk * nip,), dtype=torch.complex128, device=dev)
             fx = fx_k.view(nkpt, blk, nip)
             ops.gram_conja(f_k, xip, out=fx)                                  # :76
-            ops.ktransform_square(fx, blk * nip, nip, theta, nipP * ncol, 1, ncol, g0 - g_lo, blk, nip, kmesh, uax,
-                                  conj2=0, out_g_fast=1, qslot=qslot, rowmap=rowmap, rowmap_sq=nip,
-                                  diag=diag[2:4])                             # :79-85
+            if fit == "gelsy":
+                if y_blk is None or y_blk.numel() != nq * nip * blk:
+                    y_blk = torch.empty((nq * nip * blk,), dtype=torch.complex128, device=dev)
+                yv = y_blk.view(nq, nip, blk)
+                ops.ktransform_square(fx, blk * nip, nip, yv, nip * blk, 1, blk, 0, blk, nip, kmesh, uax,
+                                      conj2=0, out_g_fast=1, qslot=qslot, diag=diag[2:4])                  # :79-85
+                c0 = g0 - g_lo
+                ops.gemm_hn_strided(q1s, yv, theta[:, :, c0:c0 + blk])
+            else:
+                ops.ktransform_square(fx, blk * nip, nip, theta, nipP * ncol, 1, ncol, g0 - g_lo, blk, nip, kmesh, uax,
+                                      conj2=0, out_g_fast=1, qslot=qslot, rowmap=rowmap, rowmap_sq=nip,
+                                      diag=diag[2:4])                             # :79-85
         _log(df_obj, "finished aoR_loop[%8d:%8d]", g0, g1)
+    del y_blk
     del fx_k
     df_obj._ao_tables_dev = None
     mark("rhs")
 
-    # ---- C(b). Theta_q = A_q^+ Y_q^T by two blocked triangular sweeps, all q at once  :108
-    lfwd, ubwd = lfwd_g.result(), ubwd_g.result()
-    del lfwd_g, ubwd_g
+    # ---- C(b). Theta_q = A_q^+ Y_q^T, all q at once                                        :108
     rmax = int(rank_h.max())
-    ops.trsm_sweeps(lfwd, ubwd, theta, nact=rmax)     # rows at positions >= max rank are zero and stay zero
-    del lfwd, ubwd
+    if fit == "gelsy":
+        # ztrsm of zgelsy: Theta~ = T11^-1 (Q1^H Y^T), here with T11 = D U^H (lower triangular) -> forward substitution;
+        # Theta = E Theta~ is never formed: W_q = E (Theta~ K Theta~^H) E^H with orthonormal E
+        lfwd = lfwd_g.result()
+        del lfwd_g, q1s
+        ops.trsm_sweep(lfwd, theta, nact=rmax, backward=False, ng=ncol)
+        del lfwd
+    else:
+        lfwd, ubwd = lfwd_g.result(), ubwd_g.result()
+        del lfwd_g, ubwd_g
+        ops.trsm_sweeps(lfwd, ubwd, theta, nact=rmax)     # rows at positions >= max rank are zero and stay zero
+        del lfwd, ubwd
     mark("fit")
     if getattr(df_obj, "keep_theta", False):
         # original row order, this rank's grid columns [g_lo, g_hi)
-        df_obj._theta_dev = ops.gather_rows(theta, rowmap)[:, :, : g_hi - g_lo]
+        if fit == "gelsy":
+            ehk = ehg.result()
+            df_obj._theta_dev = ops.gemm_hn(ehk, theta)[:, :, : g_hi - g_lo]          # zunmrz + permutation of zgelsy
+        else:
+            df_obj._theta_dev = ops.gather_rows(theta, rowmap)[:, :, : g_hi - g_lo]
 
     # ---- D. Coulomb kernel                                                       :96-122
     vol = float(pcell.vol)
@@ -334,10 +401,19 @@ def build(df_obj):
         mark("fft")
         theta = sharding.to_column_layout(vecs, comm)            # [nq][nipP][ncol]
         del vecs
-    wslot = torch.zeros((nq, nip, nip), dtype=torch.complex128, device=dev)
-    nrow = min(nip, rmax)
-    ops.herk_strided(theta, ncol, nipP * ncol, nrow, ncol, 1.0, piv_q, nip, wslot, nip, nip * nip, nq)   # :121
-    sharding.allreduce_sum_(wslot, comm)
+    if fit == "gelsy":
+        wt = torch.zeros((nq, nipP, nipP), dtype=torch.complex128, device=dev)
+        ops.herk_strided(theta, ncol, nipP * ncol, rmax, ncol, 1.0, None, 0, wt, nipP, nipP * nipP, nq)      # :121
+        sharding.allreduce_sum_(wt, comm)
+        eh = ehg.result()
+        del ehg
+        wslot = ops.hermitize(ops.gemm_hn(eh, ops.gemm_nn(wt, eh)))        # W_q = E W~ E^H
+        del wt, eh
+    else:
+        wslot = torch.zeros((nq, nip, nip), dtype=torch.complex128, device=dev)
+        nrow = min(nip, rmax)
+        ops.herk_strided(theta, ncol, nipP * ncol, nrow, ncol, 1.0, piv_q, nip, wslot, nip, nip * nip, nq)   # :121
+        sharding.allreduce_sum_(wslot, comm)
     wq = torch.empty((nkpt, nip, nip), dtype=torch.complex128, device=dev)
     for s, q in enumerate(qind):
         wq[q].copy_(wslot[s])

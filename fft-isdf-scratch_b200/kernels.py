@@ -215,6 +215,166 @@ class IsdfOps:
                                                     _stream()), "isdf_trsm_sweeps")
         self.launches += 2 * (-(-nact // TB))
 
+    def trsm_sweep(self, op, t, nact=None, backward=False, ng=None):
+        """One direction: t <- U^{-H} t (op = lfwd) or t <- U^{-1} t (op = ubwd, backward=True), in place."""
+        _chk(t, c128)
+        batch, nP, ldt = t.shape
+        nact = nP if nact is None else int(nact)
+        ng = ldt if ng is None else int(ng)
+        self.handle.check(self.lib.isdf_trsm_sweep(self.h, _ptr(op), _ptr(t), nP, nact, ng, ldt, batch,
+                                                   int(bool(backward)), _stream()), "isdf_trsm_sweep")
+        self.launches += -(-nact // TB)
+
+    def chol_nopivot(self, a, tol=0.0, nb=32):
+        """Unpivoted Cholesky a = U^H U of [batch, n, n] Hermitian matrices (lower triangle read, destroyed);
+        stops at the first pivot <= tol.  Returns (u [batch, n, n], piv (identity), rank)."""
+        _chk(a, c128)
+        batch, n, _ = a.shape
+        u = torch.empty((batch, n, n), dtype=c128, device=self.device)
+        piv = torch.empty((batch, n), dtype=torch.int32, device=self.device)
+        rank = torch.empty((batch,), dtype=torch.int32, device=self.device)
+        nbytes = C.c_size_t()
+        self.lib.isdf_pchol_workspace_bytes(n, batch, C.byref(nbytes))
+        work = torch.empty((nbytes.value,), dtype=torch.uint8, device=self.device)
+        self.handle.check(self.lib.isdf_chol_nopivot(self.h, _ptr(a), n, batch, n, float(tol), int(nb), _ptr(u), n,
+                                                     _ptr(piv), _ptr(rank), _ptr(work), _stream()),
+                          "isdf_chol_nopivot")
+        self.launches += 3 + 2 * max(1, -(-n // nb))
+        return u, piv, rank
+
+    # ---- K5 (reference semantics): LAPACK zgelsy restated on the device (fftisdf.py:108) ---------------
+    def qrcp(self, w):
+        """Householder QR with column pivoting (zgeqp3) of [batch, n, n] matrices held COLUMN-major
+        (w[b, c, i] = A[i, c]); w is overwritten (w[b, c, k] = R[k, c] for k <= pos[c]).
+        Returns (vt [batch, n, n] reflectors by row, tau [batch, n], piv, pos)."""
+        _chk(w, c128)
+        batch, n, _ = w.shape
+        vt = torch.empty((batch, n, n), dtype=c128, device=self.device)
+        tau = torch.empty((batch, n), dtype=c128, device=self.device)
+        piv = torch.empty((batch, n), dtype=torch.int32, device=self.device)
+        pos = torch.empty((batch, n), dtype=torch.int32, device=self.device)
+        self.handle.check(self.lib.isdf_qrcp(self.h, _ptr(w), n, batch, _ptr(vt), _ptr(tau), _ptr(piv), _ptr(pos),
+                                             _stream()), "isdf_qrcp")
+        self.launches += 2
+        return vt, tau, piv, pos
+
+    def gelsy_rank(self, w, piv, rcond):
+        batch, n, _ = w.shape
+        rank = torch.empty((batch,), dtype=torch.int32, device=self.device)
+        xwork = torch.empty((batch, 2, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gelsy_rank(self.h, _ptr(w), _ptr(piv), n, batch, float(rcond), _ptr(xwork),
+                                                   _ptr(rank), _stream()), "isdf_gelsy_rank")
+        self.launches += 1
+        return rank
+
+    def gemm_tn(self, a, b):
+        """out[z] = a[z]^T @ b[z] (no conjugation); a [batch,k,m] (row pitch a.stride(1)), b [batch,k,n]."""
+        assert a.dtype == c128 and b.dtype == c128 and a.stride(2) == 1 and b.stride(2) == 1
+        batch, k, m = a.shape
+        n = b.shape[2]
+        out = torch.empty((batch, m, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gemm_tn(self.h, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1),
+                                                b.stride(0), _ptr(out), n, m * n, m, n, k, batch, _stream()),
+                          "isdf_gemm_tn")
+        self.launches += 1
+        return out
+
+    def gemm_hn_strided(self, a, b, out):
+        """out[z] = a[z]^H @ b[z] into a strided view: a [batch,k,m], b [batch,k,n], out [batch,m,n] (unit last stride)."""
+        assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
+        batch, k, m = a.shape
+        n = b.shape[2]
+        self.handle.check(self.lib.isdf_gemm_hn(self.h, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1),
+                                                b.stride(0), _ptr(out), out.stride(1), out.stride(0), m, n, k, batch,
+                                                _stream()), "isdf_gemm_hn")
+        self.launches += 1
+        return out
+
+    def hermitize(self, w):
+        _chk(w, c128)
+        batch, n, _ = w.shape
+        self.handle.check(self.lib.isdf_hermitize(self.h, _ptr(w), n, batch, _stream()), "isdf_hermitize")
+        self.launches += 1
+        return w
+
+    def gelsy_qr(self, a_q, rcond):
+        """Stage 1 of the gelsy fit for Hermitian a_q [batch, n, n] (row-major): QRCP + rank decision.
+        Returns a state dict (device tensors); `rank` is still on the device."""
+        _chk(a_q, c128)
+        w = torch.empty_like(a_q)
+        self.conj_copy(a_q, w)                    # column-major working copy: w[c][i] = A[i][c] = conj(A[c][i])
+        vt, tau, piv, pos = self.qrcp(w)
+        rank = self.gelsy_rank(w, piv, rcond)
+        return dict(w=w, vt=vt, tau=tau, piv=piv, pos=pos, rank=rank)
+
+    def gelsy_operators(self, st, rP):
+        """Stage 2: the three dense operators of x = P Z^H [T11^-1 (Q^H b)(:rank); 0] for every matrix of the batch:
+             q1s  [batch, n, rP]   Q1 D^-1 (orthonormal columns scaled by 1/|R_kk|, zero beyond rank)
+             lfwd [batch, rP, rP]  block operator of the forward substitution with U^H, D^-1 [R11 R12] P^T = U^H E^H
+             eh   [batch, rP, n]   E^H (orthonormal rows, zero beyond rank)
+           so that  Theta~ = U^-H (q1s^H Y^T)  [rank x ng]  and  Theta = eh^H Theta~,  W = eh^H W~ eh."""
+        w, vt, tau, piv, pos, rank = st["w"], st["vt"], st["tau"], st["piv"], st["pos"], st["rank"]
+        batch, n, _ = w.shape
+        assert rP % TB == 0
+        kk = min(rP, n)
+        ident = torch.arange(rP, dtype=torch.int32, device=self.device).repeat(batch, 1).contiguous()
+        # --- Q1 through the compact-WY form of the first `rank` reflectors
+        vv = vt[:, :kk, :]
+        g = torch.zeros((batch, rP, rP), dtype=c128, device=self.device)
+        self.gram_conja_strided(vv, vv, g[:, :kk, :kk])                      # V^H V
+        s = torch.empty((batch, rP, rP), dtype=c128, device=self.device)
+        m = torch.empty((batch, rP, rP), dtype=c128, device=self.device)
+        dinv = torch.empty((batch, rP), dtype=torch.float64, device=self.device)
+        self.handle.check(self.lib.isdf_gelsy_extract(self.h, _ptr(g), _ptr(tau), _ptr(rank), _ptr(vt), _ptr(w),
+                                                      _ptr(piv), n, rP, batch, _ptr(s), _ptr(m), _ptr(dinv),
+                                                      _stream()), "isdf_gelsy_extract")
+        self.launches += 1
+        _, ub = self.trsm_prepare(s, ident, rank, rP)
+        self.trsm_sweep(ub, m, backward=True)                                 # M = S^-1 V1^H
+        del s, ub, g
+        q1s = torch.zeros((batch, n, rP), dtype=c128, device=self.device)
+        self.gemm_tn_into(vv, m[:, :kk, :], q1s)                              # V M
+        del m
+        self.handle.check(self.lib.isdf_gelsy_q1_finish(self.h, _ptr(q1s), _ptr(dinv), _ptr(rank), n, rP, batch,
+                                                        _stream()), "isdf_gelsy_q1_finish")
+        self.launches += 1
+        # --- E^H and the triangular factor: Cholesky-QR (twice) of the row-scaled [R11 R12] P^T
+        eh = torch.empty((batch, rP, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gelsy_rhat(self.h, _ptr(w), _ptr(pos), _ptr(dinv), _ptr(rank), n, rP, batch,
+                                                   _ptr(eh), _stream()), "isdf_gelsy_rhat")
+        self.launches += 1
+        us = []
+        for _ in range(2):
+            gg = self.herk(eh)
+            u, _, rk = self.chol_nopivot(gg)
+            lf, _ = self.trsm_prepare(u, ident, rk, rP)
+            self.trsm_sweep(lf, eh, backward=False)
+            us.append(u)
+            del gg, lf
+        ucomb = self.gemm_nn(us[1], us[0])                                    # U = U2 U1
+        lfwd, _ = self.trsm_prepare(ucomb, ident, rank, rP)
+        return dict(q1s=q1s, lfwd=lfwd, eh=eh, chol_rank=rk)
+
+    def gram_conja_strided(self, a, b, out):
+        assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
+        batch, m, k = a.shape
+        n = b.shape[1]
+        self.handle.check(self.lib.isdf_gram_conja(self.h, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1),
+                                                   b.stride(0), _ptr(out), out.stride(1), out.stride(0), m, n, k,
+                                                   batch, _stream()), "isdf_gram_conja")
+        self.launches += 1
+        return out
+
+    def gemm_tn_into(self, a, b, out):
+        assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
+        batch, k, m = a.shape
+        n = b.shape[2]
+        self.handle.check(self.lib.isdf_gemm_tn(self.h, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1),
+                                                b.stride(0), _ptr(out), out.stride(1), out.stride(0), m, n, k, batch,
+                                                _stream()), "isdf_gemm_tn")
+        self.launches += 1
+        return out
+
     # ---- K6: batched 3-D FFT with fused phase / weight ----------------------------------------
     @staticmethod
     def _max_prime_factor(n):

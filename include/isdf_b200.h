@@ -123,6 +123,45 @@ int isdf_trsm_prepare(void* handle, const void* u, int ldu_rows, const int* piv,
 int isdf_trsm_sweeps(void* handle, const void* lfwd, const void* ubwd, void* t, int nP, int nact, long ng, long ldt, int batch,
                      void* stream);
 
+/* One direction of the above: backward = 0: T <- U^{-H} T with op = lfwd; backward = 1: T <- U^{-1} T with op = ubwd. */
+int isdf_trsm_sweep(void* handle, const void* op, void* t, int nP, int nact, long ng, long ldt, int batch,
+                    int backward, void* stream);
+/* Unpivoted Cholesky A = U^H U (same kernels and argument meaning as isdf_pchol, pivot = next position; piv
+ * comes back as the identity).  Stops at the first pivot <= tol. */
+int isdf_chol_nopivot(void* handle, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
+                      int ldu_rows, int* piv, int* rank, void* workspace, void* stream);
+
+/* fftisdf.py:108  scipy.linalg.lstsq(x4_q, y_q.T, lapack_driver="gelsy") -> LAPACK ZGELSY, restated on the device.
+ *
+ * isdf_qrcp (zgeqp3): Householder QR with column pivoting, A P = Q R.  a [batch][n][n] is the COLUMN-major working
+ * copy (a[c][i] = A[i][c]; for the Hermitian metric this is conj of the row-major matrix); on return
+ * a[c][k] = R[k][c] for k <= pos[c].  vt [batch][n][n]: row k = Householder vector v_k (v_k[k] = 1, zeros before;
+ * an identity reflector is the zero row).  tau [batch][n] c128 (H_k = I - tau_k v_k v_k^H, LAPACK's convention).
+ * piv [batch][n] position -> column, pos [batch][n] column -> position (both 0-based, device).
+ * isdf_gelsy_rank (zgelsy's loop over zlaic1): rank[b] = number of leading columns of R accepted by incremental
+ * condition estimation, smax * rcond <= smin (the reference gets rcond = machine eps from scipy).  xwork: 2*batch*n
+ * c128. */
+int isdf_qrcp(void* handle, void* a, int n, int batch, void* vt, void* tau, int* piv, int* pos, void* stream);
+int isdf_gelsy_rank(void* handle, const void* a, const int* piv, int n, int batch, double rcond, void* xwork,
+                    int* rank, void* stream);
+/* Ingredients of the three dense operators through which zgelsy's solution x = P Z^H [T11^-1 (Q^H b)(1:rank); 0]
+ * (zunmqr, ztrsm, ztzrzf/zunmrz) is applied to all right-hand sides (sequenced by kernels.py:gelsy_factor):
+ *   Q1 D^-1  = (I(:, :rank) - V S^-1 V(:rank, :)^H) D^-1,  S = diag(1/tau) + striu(V^H V)   (compact WY, D = |diag R|)
+ *   E^H      = rows of D^-1 [R11 R12] P^T orthonormalised by Cholesky-QR (twice), U = their triangular factor
+ * isdf_gelsy_extract: g [batch][rP][rP] = V^H V  ->  s, v1h [batch][rP][rP] (S and V(:rank,:)^H), dinv [batch][rP].
+ * isdf_gelsy_rhat: rhat [batch][rP][n] = D^-1 [R11 R12] P^T (original column order, zero rows beyond rank).
+ * isdf_gelsy_q1_finish: vm [batch][n][rP] = V S^-1 V1^H on entry, Q1 D^-1 on return (zero columns beyond rank).
+ * isdf_hermitize: w <- (w + w^H)/2.  isdf_gemm_tn: c = a^T b (no conjugation), a [k][m], b [k][n]. */
+int isdf_gelsy_extract(void* handle, const void* g, const void* tau, const int* rank, const void* vt, const void* a,
+                       const int* piv, int n, int rP, int batch, void* s, void* v1h, double* dinv, void* stream);
+int isdf_gelsy_rhat(void* handle, const void* a, const int* pos, const double* dinv, const int* rank, int n, int rP,
+                    int batch, void* rhat, void* stream);
+int isdf_gelsy_q1_finish(void* handle, void* vm, const double* dinv, const int* rank, int n, int rP, int batch,
+                         void* stream);
+int isdf_hermitize(void* handle, void* w, int n, int batch, void* stream);
+int isdf_gemm_tn(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB, void* c,
+                 long ldc, long strideC, int m, int n, int k, int batch, void* stream);
+
 /* fftisdf.py:113-115  pbctools.fft(z_q * fq, mesh) * coulG * vol/ngrid  (the ifft at :118 is removed by
  * Parseval):  data [nvec][ldv >= ng] in place, out[v][G] = post[G] * sum_r data[v][r] pre[r] e^{-iG.r}.
  * mesh[3] host; pre [ng] c128 or NULL; post [ng] f64 or NULL; group_vecs <= 0 picks an L2-sized group. */

@@ -12,6 +12,7 @@ restatement of fftisdf.py:22-228,357-388; it cannot pin PySCF's own helpers (una
 """
 import importlib.util
 import os
+import re
 import sys
 import types
 
@@ -23,6 +24,8 @@ REF = os.environ.get("ISDF_REFERENCE_DIR", "/root/reference")
 sys.path.insert(0, ROOT)
 
 from oracle import pbc_helpers as H  # noqa: E402
+
+GELSY_RANKS = {}   # q -> rank, filled from the reference's own log line during build()
 
 
 def _install_stubs():
@@ -66,6 +69,10 @@ def _install_stubs():
         debug = info
 
         def timer(self, msg, *t0):
+            # the reference reports zgelsy's rank only through this message (fftisdf.py:122)
+            m = re.match(r"w\[\s*(\d+)\], rank =\s*(\d+) /", msg)
+            if m:
+                GELSY_RANKS[int(m.group(1))] = int(m.group(2))
             return (time.process_time(), time.perf_counter())
 
     logger.new_logger = lambda obj=None, verbose=None: _Log()
@@ -166,6 +173,9 @@ CASES = {
     # reference's own zgelsy output only reproduces to ~1e-8)
     "k333_odd": dict(mesh=[7, 7, 9], nao=8, seed=17, kmesh=[3, 3, 3], m0=[5, 5, 5], c0=2.5, ltypes="spd", blksize=200,
                      skew=True),
+    # mid-size RANK-DEFICIENT case (the regime of the reference's defaults: nip = nao*c0 beyond the local pair rank,
+    # zgelsy truncates every A_q), odd FFT mesh; the reference's per-q ranks are stored next to its outputs
+    "k221_rd": dict(mesh=[11, 11, 13], nao=10, seed=31, kmesh=[2, 2, 1], m0=[8, 8, 8], c0=12.0, ltypes="sp", blksize=600),
     "k434_odd": dict(mesh=[5, 7, 5], nao=8, seed=17, kmesh=[4, 3, 4], m0=[4, 5, 4], c0=2.5, ltypes="spd", blksize=8000,
                      skew=True),
 }
@@ -203,7 +213,9 @@ def run_case(ref, name, spec):
     ref.cell = cell  # fftisdf.py:322 reads the *global* `cell`
     df = ref.ISDF(cell, kpts, m0=spec["m0"], c0=spec["c0"])
     df.blksize = spec["blksize"]
+    GELSY_RANKS.clear()
     df.build()
+    ranks = np.asarray([GELSY_RANKS[q] for q in range(len(kpts))])
     x0 = np.asarray(cell.pbc_eval_gto("GTOval", cell.gen_uniform_grids(spec["m0"]), kpts=df.kpts))
     coord = df.grids.coords
     f_all = np.asarray(cell.pbc_eval_gto("GTOval", coord, kpts=df.kpts))
@@ -223,10 +235,10 @@ def run_case(ref, name, spec):
     vk = ref.get_k_kpts(df, dm, 1, df.kpts, None)
     out = dict(a=cell.a, kpts=df.kpts, kmesh=np.asarray(kmesh), mesh=np.asarray(spec["mesh"]),
                m0=np.asarray(spec["m0"]), c0=spec["c0"], blksize=spec["blksize"], x0=x0, f_all=f_all,
-               coord=coord, x=df._x, wq=df._wq, w0=df._w0, mask=np.asarray(mask), dm=dm, vj=vj, vk=vk)
+               coord=coord, x=df._x, wq=df._wq, w0=df._w0, mask=np.asarray(mask), dm=dm, vj=vj, vk=vk, ranks=ranks)
     path = os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz")
     np.savez_compressed(path, **out)
-    print(f"{name}: nk={nk} nip={nip} nao={nao} ng={len(coord)} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
+    print(f"{name}: nk={nk} nip={nip} nao={nao} ng={len(coord)} ranks={ranks.tolist()} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
 
 
 def _time_reversal(kmesh):

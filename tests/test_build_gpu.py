@@ -5,9 +5,10 @@ Tolerances (FP64, relative to the largest reference entry):
   * interpolation-point indices: identical.
   * A_q numerically full rank (cond <~ 1e6): Theta, W_q, J, K, E_x within 1e-10 (north-star bar).
   * cond ~ 1e8 (gamma_s): 1e-8 on Theta/W (forward error ~ cond*eps of either solver), 1e-10 on J/K.
-  * rank-deficient A_q (k222_sp, the regime the reference's c0 default lands in): gelsy's own result
-    moves by ~1e-6 under an eps-level perturbation of A_q (oracle/README), so W/Theta are not
-    comparable; J/K are checked against the oracle's measured noise floor.
+  * rank-deficient A_q (k222_sp, k221_rd: the regime the reference's c0 default lands in): the device zgelsy takes the
+    reference's rank decision q by q; K, J, E_x and the reconstructed ERIs within 10x of the reference's own
+    reproducibility floor (its result under a 1e-16 perturbation of A_q: ~6e-7 on K), and the reference's ERI
+    acceptance test (vs exact pair densities) for both arms.
 """
 import os
 
@@ -84,34 +85,109 @@ def test_time_reversal_shortcut_equals_full_computation():
     assert len(df3._qind) == len(g["kpts"])
 
 
-def test_rank_deficient_case_against_oracle_noise_floor():
-    g, df = run_golden("k222_sp")
+def _momentum_quadruples(kmesh, nk, stride3=1):
+    import itertools
+    kidx = np.array(list(itertools.product(*[range(n) for n in kmesh])))
+    find = lambda v: int(np.where((kidx == np.mod(v, kmesh)).all(1))[0][0])
+    for k1 in range(nk):
+        for k2 in range(nk):
+            q = find(kidx[k2] - kidx[k1])
+            for k3 in range(0, nk, stride3):
+                yield k1, k2, k3, find(kidx[k3] - kidx[q]), q
+
+
+def _eri_rel_to_reference(x, wq, wq_ref, kmesh):
+    """max relative deviation of the reconstructed ERIs (fftdf-with-k-lstsq.py:232) from those of the reference's W."""
+    worst = 0.0
+    for k1, k2, k3, k4, q in _momentum_quadruples(kmesh, len(x)):
+        e1 = O.eri_from_w(wq[q], x[k1], x[k2], x[k3], x[k4])
+        e0 = O.eri_from_w(wq_ref[q], x[k1], x[k2], x[k3], x[k4])
+        worst = max(worst, rel(e1, e0))
+    return worst
+
+
+def _eri_error_vs_exact(x, wq, g, kmesh):
+    """The reference's acceptance test (fftdf-with-k-lstsq.py:219-258): reconstructed ERIs against the exact ERIs of the
+    same pair densities on the dense grid (PySCF-free stand-in for FFTDF.get_eri), worst relative error."""
+    a, kpts, mesh, coord, phi = g["a"], g["kpts"], g["mesh"].tolist(), g["coord"], g["f_all"]
+    ng, vol = len(coord), abs(np.linalg.det(g["a"]))
+    worst, cache = 0.0, {}
+    for k1, k2, k3, k4, q in _momentum_quadruples(kmesh, len(x)):
+        if (k1, k2) not in cache:
+            cache.clear()
+            fq = np.exp(-1j * coord @ kpts[q])
+            rho12 = np.einsum("gm,gn->mng", phi[k1].conj(), phi[k2]).reshape(-1, ng)
+            cache[(k1, k2)] = H.ifft(H.fft(rho12 * fq, mesh) * H.get_coulG(a, kpts[q], mesh) * vol / ng, mesh) * fq.conj()
+        rho34 = np.einsum("gk,gl->klg", phi[k3].conj(), phi[k4]).reshape(-1, ng)
+        eri_ref = cache[(k1, k2)] @ rho34.T
+        eri = O.eri_from_w(wq[q], x[k1], x[k2], x[k3], x[k4]).reshape(eri_ref.shape)
+        worst = max(worst, float(np.abs(eri - eri_ref).max() / np.abs(eri_ref).max()))
+    return worst
+
+
+def _reference_noise_floor(g, out, nrep=3):
+    """How far the REFERENCE's own result moves when A_q is perturbed at the 1e-16 level before its lstsq(gelsy) call
+    (fftisdf.py:108): max over nrep perturbations of the relative change of K, J and the reconstructed ERIs.  This is
+    the reproducibility floor of the reference in the rank-deficient regime (another BLAS would move it as much)."""
+    a, kpts, kmesh, mesh = g["a"], g["kpts"], g["kmesh"].tolist(), g["mesh"].tolist()
+    ph, gv, vol, ng = H.get_phase(a, kpts, kmesh), H.get_Gv(a, mesh), abs(np.linalg.det(a)), len(g["coord"])
+    dms = g["dm"][None]
+    vk_ref, vj_ref = g["vk"].reshape(g["dm"].shape), g["vj"].reshape(g["dm"].shape)
+    fk = fj = fe = 0.0
+    for rep in range(nrep):
+        rng = np.random.default_rng(1000 + rep)
+        wq2 = []
+        for q in range(len(kpts)):
+            aq = out["x4_k"][q] * (1.0 + 1e-16 * rng.standard_normal(out["x4_k"][q].shape))
+            th = scipy.linalg.lstsq(aq, out["y"][q].T, lapack_driver="gelsy")[0]
+            fq = np.exp(-1j * g["coord"] @ kpts[q])
+            b = H.fft(th * fq, mesh) * np.sqrt(H.get_coulG(a, kpts[q], mesh, Gv=gv) * vol) / ng
+            wq2.append(b @ b.conj().T)
+        wq2 = np.asarray(wq2)
+        fk = max(fk, rel(O.get_k_kpts(out["x"], wq2, dms, ph)[0], vk_ref))
+        fj = max(fj, rel(O.get_j_kpts(out["x"], wq2[0], dms)[0], vj_ref))
+        fe = max(fe, _eri_rel_to_reference(out["x"], wq2, g["wq"], kmesh))
+    return fk, fj, fe
+
+
+@pytest.mark.parametrize("name", ["k222_sp", "k221_rd"])
+def test_rank_deficient_cases_at_the_reference_noise_floor(name):
+    """Rank-deficient A_q -- the regime the reference's defaults land in (nip = nao*c0 beyond the local pair rank; the
+    author logs `rank / nip`, fftisdf.py:122).  The device zgelsy must take the reference's rank decision, and K, J,
+    E_x and the reconstructed ERIs must sit within 10x of the reference's own eps-perturbation floor."""
+    g, df = run_golden(name)
     nip = df._x.shape[1]
-    assert np.array_equal(df._mask, g["mask"])
-    assert all(int(r) < nip for r in df._ranks)                # truncated, like gelsy's rank < nip
+    kmesh = g["kmesh"].tolist()
+    assert np.array_equal(df._mask, g["mask"]) and np.array_equal(df._x, g["x"])
+    assert all(int(r) < nip for r in g["ranks"])
+    ranks = np.zeros(len(g["kpts"]), dtype=int)
+    tr = __import__("fft_isdf_scratch_b200").pbc_tools.time_reversal_partner(kmesh)
+    for s, q in enumerate(df._qind):
+        ranks[q] = ranks[tr[q]] = df._ranks[s]
+    assert np.array_equal(ranks, g["ranks"]), (ranks, g["ranks"])        # zgelsy's rank, q by q
     w = df._wq
     for q in range(len(w)):
-        assert np.abs(w[q] - w[q].conj().T).max() == 0.0       # exactly Hermitian
-    # the oracle's own sensitivity: gelsy with rcond 1e-15 instead of eps
-    a, kpts, kmesh, mesh = g["a"], g["kpts"], g["kmesh"].tolist(), g["mesh"].tolist()
-    out = O.build(a, kpts, kmesh, mesh, g["x0"], g["f_all"], g["coord"], float(g["c0"]))
-    ph = H.get_phase(a, kpts, kmesh)
-    gv = H.get_Gv(a, mesh)
-    vol = abs(np.linalg.det(a))
-    ng = len(g["coord"])
-    wq2 = []
-    for q in range(len(kpts)):
-        th = scipy.linalg.lstsq(out["x4_k"][q], out["y"][q].T, cond=1e-15, lapack_driver="gelsy")[0]
-        fq = np.exp(-1j * g["coord"] @ kpts[q])
-        b = H.fft(th * fq, mesh) * np.sqrt(H.get_coulG(a, kpts[q], mesh, Gv=gv) * vol) / ng
-        wq2.append(b @ b.conj().T)
-    dms = g["dm"][None]
-    vk_ref = g["vk"].reshape(g["dm"].shape)
-    vk_alt = O.get_k_kpts(out["x"], np.asarray(wq2), dms, ph)[0]
-    floor = rel(vk_alt, vk_ref)
+        assert np.abs(w[q] - w[q].conj().T).max() == 0.0                  # exactly Hermitian
+    out = O.build(g["a"], g["kpts"], kmesh, g["mesh"].tolist(), g["x0"], g["f_all"], g["coord"], float(g["c0"]))
+    assert list(out["ranks"]) == list(g["ranks"])
+    fk, fj, fe = _reference_noise_floor(g, out)
     vj, vk = df.get_jk(g["dm"], kpts=g["kpts"])
-    assert rel(vk, vk_ref) < max(10 * floor, 1e-6)
-    assert rel(vj, g["vj"].reshape(vj.shape)) < max(10 * floor, 1e-6)
+    dk, dj = rel(vk, g["vk"].reshape(vk.shape)), rel(vj, g["vj"].reshape(vj.shape))
+    de = _eri_rel_to_reference(g["x"], w, g["wq"], kmesh)
+    print(f"\n{name}: K {dk:.2e} (floor {fk:.2e})  J {dj:.2e} (floor {fj:.2e})  ERI {de:.2e} (floor {fe:.2e})")
+    assert dk < 10 * fk and dj < 10 * fj and de < 10 * fe, (dk, fk, dj, fj, de, fe)
+    shp = (1,) + g["dm"].shape
+    ex_ref = O.exchange_energy(g["vk"].reshape(shp), g["dm"].reshape(shp))
+    ex = O.exchange_energy(np.asarray(vk).reshape(shp), g["dm"].reshape(shp))
+    assert abs(ex - ex_ref) < 10 * fk * abs(ex_ref)
+    # the reference's own acceptance test, both arms: ERIs against the exact pair densities
+    e_gpu, e_ref = _eri_error_vs_exact(g["x"], w, g, kmesh), _eri_error_vs_exact(g["x"], g["wq"], g, kmesh)
+    print(f"{name}: ERI vs exact  device {e_gpu:.3e}  reference {e_ref:.3e}")
+    assert e_gpu <= 2 * e_ref and e_gpu < 1e-3      # (this tiny cell's ISDF error itself is 3e-4 / 2e-5)
+    # the cheaper rank-revealing Cholesky route (fit = "cholesky") is NOT held to this bar: it truncates differently
+    _, dfc = run_golden(name, fit="cholesky")
+    vjc, vkc = dfc.get_jk(g["dm"], kpts=g["kpts"])
+    assert rel(vkc, g["vk"].reshape(vkc.shape)) < 1e-3 and _eri_error_vs_exact(g["x"], dfc._wq, g, kmesh) < 1e-3
 
 
 def test_synthetic_cell_end_to_end_vs_oracle():

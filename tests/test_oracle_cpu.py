@@ -227,3 +227,57 @@ def test_trans_2e_matches_definition_for_general_orbitals():
     assert eri_u.shape == (1, nlo, nlo, nlo, nlo) and np.abs(eri_u[0] - ref_u).max() < 1e-12 * np.abs(ref_u).max()
     with pytest.raises(NotImplementedError):
         E.trans_2e(df, kscaled_center=[0.5, 0.0, 0.0])
+
+
+# ---- oracle/gelsy_port.py (numpy restatement of LAPACK zgelsy) pinned against the real LAPACK through scipy ----------
+def _graded_psd(n, r, seed, decay):
+    rng = np.random.default_rng(seed)
+    c = rng.standard_normal((r, n)) + 1j * rng.standard_normal((r, n))
+    c *= 10.0 ** (-decay * np.arange(r) / max(r - 1, 1))[:, None]
+    return c.conj().T @ c
+
+
+@pytest.mark.parametrize("n,seed", [(7, 1), (40, 2), (90, 3)])
+def test_gelsy_port_qrcp_matches_zgeqp3(n, seed):
+    import scipy.linalg
+    from oracle import gelsy_port as GP
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    a *= (1.0 + np.arange(n))[None, ::-1] ** 0.5
+    qr, tau, jp = GP.qrcp(a)
+    qr2, jp2, tau2, _, _ = scipy.linalg.lapack.zgeqp3(a)
+    assert np.array_equal(jp, jp2 - 1)
+    assert np.abs(np.triu(qr) - np.triu(qr2)).max() < 1e-12 * np.abs(qr2).max()
+    assert np.abs(tau - tau2).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,r,decay,seed", [(12, 12, 1.0, 1), (40, 25, 5.0, 2), (60, 60, 7.5, 3), (80, 50, 9.0, 4),
+                                             (57, 6, 1.0, 5)])
+def test_gelsy_port_rank_and_solution_match_scipy_gelsy(n, r, decay, seed):
+    import scipy.linalg
+    from oracle import gelsy_port as GP
+    a = _graded_psd(n, r, seed, decay)
+    rng = np.random.default_rng(seed + 50)
+    b = a @ (rng.standard_normal((n, 4)) + 1j * rng.standard_normal((n, 4)))
+    ref = scipy.linalg.lstsq(a, b, lapack_driver="gelsy")
+    x, rank = GP.gelsy(a, b)
+    assert rank == ref[2]
+    f = GP.gelsy_factor(a)
+    assert np.abs(f["q1"].conj().T @ f["q1"] - np.eye(rank)).max() < 1e-13
+    assert np.abs(f["e"].conj().T @ f["e"] - np.eye(rank)).max() < 1e-13
+    # same rank + same algorithm: the minimum-norm solutions agree to the conditioning of the kept block
+    d = np.abs(np.diag(f["r"]))[:rank]
+    assert np.abs(x - ref[0]).max() < max(1e-11, 100 * d[0] / d[-1] * 2.2e-16) * np.abs(ref[0]).max()
+    assert np.abs(a @ x - b).max() < 1e-9 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("name", ["k222_sp", "k221_rd"])
+def test_gelsy_port_reproduces_the_reference_ranks(name):
+    """The per-q ranks the REFERENCE logged (fftisdf.py:122, stored in the golden by gen_golden.py) come out of the
+    port's QRCP + incremental condition estimation on the same A_q."""
+    from oracle import gelsy_port as GP
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz"))
+    ph = H.get_phase(g["a"], g["kpts"], g["kmesh"].tolist())
+    x4_k = O.build_metric(g["x"], ph)
+    ranks = [GP.gelsy_factor(x4_k[q])["rank"] for q in range(len(x4_k))]
+    assert ranks == g["ranks"].tolist()

@@ -249,20 +249,39 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
       }
       __syncthreads();
       const cplx tau = bc[par].tau;
-      // GEMV, warp per live column:  sdot[c] = sum_{i>=k} conj(a_c[i]) v_k[i]
-      for (int lc = warp; lc < nown; lc += QR_NW) {
-        if (pos[lc] <= k) continue;
-        const cplx* Wc = W + (long)(c_lo + lc) * n;
-        double r0 = 0.0, i0 = 0.0, r1 = 0.0, i1 = 0.0;
+      // GEMV, warp per live column (two columns at a time, four rows per lane in flight -> 8 independent 16-byte loads
+      // per lane: the stage is latency-bound otherwise):  sdot[c] = sum_{i>=k} conj(a_c[i]) v_k[i]
+      for (int lc = warp; lc < nown; lc += 2 * QR_NW) {
+        const int lc2 = lc + QR_NW;
+        const bool live0 = pos[lc] > k;
+        const bool live1 = (lc2 < nown) && pos[lc2] > k;
+        if (!live0 && !live1) continue;
+        const cplx* W0 = W + (long)(c_lo + (live0 ? lc : lc2)) * n;
+        const cplx* W1 = W + (long)(c_lo + (live1 ? lc2 : lc)) * n;
+        double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
         int i = k + lane;
-        for (; i + 32 < n; i += 64) {
-          const cplx a = Wc[i], v = vbuf[i], a2 = Wc[i + 32], v2 = vbuf[i + 32];
-          r0 += a.x * v.x + a.y * v.y;   i0 += a.x * v.y - a.y * v.x;
-          r1 += a2.x * v2.x + a2.y * v2.y; i1 += a2.x * v2.y - a2.y * v2.x;
+        for (; i + 96 < n; i += 128) {
+          cplx a[4], c[4], v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { a[u] = W0[i + 32 * u]; c[u] = W1[i + 32 * u]; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = vbuf[i + 32 * u];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ar += a[u].x * v[u].x + a[u].y * v[u].y;  ai += a[u].x * v[u].y - a[u].y * v[u].x;
+            br += c[u].x * v[u].x + c[u].y * v[u].y;  bi += c[u].x * v[u].y - c[u].y * v[u].x;
+          }
         }
-        if (i < n) { const cplx a = Wc[i], v = vbuf[i]; r0 += a.x * v.x + a.y * v.y; i0 += a.x * v.y - a.y * v.x; }
-        r0 = warp_sum(r0 + r1); i0 = warp_sum(i0 + i1);
-        if (lane == 0) sdot[lc] = make_double2(r0, i0);
+        for (; i < n; i += 32) {
+          const cplx a = W0[i], c = W1[i], v = vbuf[i];
+          ar += a.x * v.x + a.y * v.y;  ai += a.x * v.y - a.y * v.x;
+          br += c.x * v.x + c.y * v.y;  bi += c.x * v.y - c.y * v.x;
+        }
+        ar = warp_sum(ar); ai = warp_sum(ai); br = warp_sum(br); bi = warp_sum(bi);
+        if (lane == 0) {
+          if (live0) sdot[lc] = make_double2(ar, ai);
+          if (live1) sdot[lc2] = live0 ? make_double2(br, bi) : make_double2(ar, ai);
+        }
       }
       __syncthreads();
       // per live column: F[c][t], pivot-row entry R[k][c], norm downdate
@@ -309,20 +328,40 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
           vbuf[tt * rt + ii] = __ldcg(V + (long)(j0 + tt) * n + r0 + ii);
         }
         __syncthreads();
-        for (int lc = warp; lc < nown; lc += QR_NW) {
-          if (pos[lc] < k) continue;
-          cplx* Wc = W + (long)(c_lo + lc) * n + r0;
-          for (int ii = lane; ii < rows; ii += 32) {
-            cplx acc = make_double2(0.0, 0.0);
+        // 2 columns x 2 rows per lane: each staged V element and each F element feeds two complex MACs
+        for (int lc = warp; lc < nown; lc += 2 * QR_NW) {
+          const int lc2 = lc + QR_NW;
+          const bool live0 = pos[lc] >= k;
+          const bool live1 = (lc2 < nown) && pos[lc2] >= k;
+          if (!live0 && !live1) continue;
+          const int la = live0 ? lc : lc2, lb = live1 ? lc2 : lc;
+          cplx* Wa = W + (long)(c_lo + la) * n + r0;
+          cplx* Wb = W + (long)(c_lo + lb) * n + r0;
+          for (int ii = lane; ii < rows; ii += 64) {
+            const int i2 = ii + 32;
+            const bool two = i2 < rows;
+            cplx a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+            // issue the global loads first: their latency overlaps the t-loop
+            cplx w0 = Wa[ii], u0 = Wb[ii];
+            cplx w1 = two ? Wa[i2] : a0, u1 = two ? Wb[i2] : a0;
             for (int tt = 0; tt < t; ++tt) {
-              const cplx vv = vbuf[tt * rt + ii];
-              const cplx f = Ft[(long)tt * ncc + lc];
-              acc.x += vv.x * f.x + vv.y * f.y;
-              acc.y += vv.y * f.x - vv.x * f.y;
+              const cplx v0 = vbuf[tt * rt + ii];
+              const cplx v1 = two ? vbuf[tt * rt + i2] : make_double2(0.0, 0.0);
+              const cplx fa = Ft[(long)tt * ncc + la];
+              const cplx fb = Ft[(long)tt * ncc + lb];
+              a0.x += v0.x * fa.x + v0.y * fa.y;  a0.y += v0.y * fa.x - v0.x * fa.y;   // v conj(f)
+              a1.x += v1.x * fa.x + v1.y * fa.y;  a1.y += v1.y * fa.x - v1.x * fa.y;
+              b0.x += v0.x * fb.x + v0.y * fb.y;  b0.y += v0.y * fb.x - v0.x * fb.y;
+              b1.x += v1.x * fb.x + v1.y * fb.y;  b1.y += v1.y * fb.x - v1.x * fb.y;
             }
-            cplx a = Wc[ii];
-            a.x -= acc.x; a.y -= acc.y;
-            Wc[ii] = a;
+            w0.x -= a0.x; w0.y -= a0.y;
+            Wa[ii] = w0;
+            if (two) { w1.x -= a1.x; w1.y -= a1.y; Wa[i2] = w1; }
+            if (live0 && live1) {
+              u0.x -= b0.x; u0.y -= b0.y;
+              Wb[ii] = u0;
+              if (two) { u1.x -= b1.x; u1.y -= b1.y; Wb[i2] = u1; }
+            }
           }
         }
       }

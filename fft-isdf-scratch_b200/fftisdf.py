@@ -212,11 +212,6 @@ def build(df_obj):
         if mine:
             qr_state = ops.gelsy_qr(a_mine, rcond if rcond > 0 else float(numpy.finfo(numpy.float64).eps))
             rank_l = qr_state["rank"]
-            # test hook: {q: rank} replaces the condition-estimation rank (to separate WHERE an eps-level plateau of
-            # |R_kk| is cut -- decided by rounding noise in LAPACK as well -- from everything else in the solver)
-            for q, r in (getattr(df_obj, "gelsy_rank_override", None) or {}).items():
-                if qslot_h[q] >= 0 and int(qslot_h[q]) in mine:
-                    rank_l[mine.index(int(qslot_h[q]))] = int(r)
         else:
             qr_state = None
             rank_l = torch.zeros((0,), dtype=torch.int32, device=dev)

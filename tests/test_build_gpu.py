@@ -126,9 +126,11 @@ def _eri_error_vs_exact(x, wq, g, kmesh):
 
 
 def _reference_noise_floor(g, out, nrep=3):
-    """How far the REFERENCE's own result moves when A_q is perturbed at the 1e-16 level before its lstsq(gelsy) call
-    (fftisdf.py:108): max over nrep perturbations of the relative change of K, J and the reconstructed ERIs.  This is
-    the reproducibility floor of the reference in the rank-deficient regime (another BLAS would move it as much)."""
+    """How far the REFERENCE's own result (scipy lstsq(gelsy), fftisdf.py:108) moves under changes that are exact
+    no-ops mathematically: A_q perturbed at the 1e-16 level, and the system permuted symmetrically (rows and columns of
+    A_q, rows of Y^T: only the summation / tie order changes, which is what another BLAS does to the reference).
+    Max over nrep variants of the relative change of K, J and the reconstructed ERIs: the reproducibility floor of
+    the reference in the rank-deficient regime."""
     a, kpts, kmesh, mesh = g["a"], g["kpts"], g["kmesh"].tolist(), g["mesh"].tolist()
     ph, gv, vol, ng = H.get_phase(a, kpts, kmesh), H.get_Gv(a, mesh), abs(np.linalg.det(a)), len(g["coord"])
     dms = g["dm"][None]
@@ -138,8 +140,13 @@ def _reference_noise_floor(g, out, nrep=3):
         rng = np.random.default_rng(1000 + rep)
         wq2 = []
         for q in range(len(kpts)):
-            aq = out["x4_k"][q] * (1.0 + 1e-16 * rng.standard_normal(out["x4_k"][q].shape))
-            th = scipy.linalg.lstsq(aq, out["y"][q].T, lapack_driver="gelsy")[0]
+            aq, yt = out["x4_k"][q], out["y"][q].T
+            if rep % 2 == 0:
+                th = scipy.linalg.lstsq(aq * (1.0 + 1e-16 * rng.standard_normal(aq.shape)), yt, lapack_driver="gelsy")[0]
+            else:
+                perm = rng.permutation(len(aq))
+                th = np.empty_like(yt)
+                th[perm] = scipy.linalg.lstsq(aq[perm][:, perm], yt[perm], lapack_driver="gelsy")[0]
             fq = np.exp(-1j * g["coord"] @ kpts[q])
             b = H.fft(th * fq, mesh) * np.sqrt(H.get_coulG(a, kpts[q], mesh, Gv=gv) * vol) / ng
             wq2.append(b @ b.conj().T)

@@ -235,7 +235,8 @@ def build(df_obj):
         nipP += TB
     if fit == "gelsy":
         if mine:
-            fac = ops.gelsy_operators(qr_state, nipP)
+            with ops.timed("gelsy_operators"):
+                fac = ops.gelsy_operators(qr_state, nipP)
             q1_l, lf_l, eh_l = fac["q1s"], fac["lfwd"], fac["eh"]
             del fac
         else:
@@ -309,16 +310,20 @@ def build(df_obj):
             for s0 in range(0, blk, sub):
                 sb = min(sub, blk - s0)
                 fxt = fx_k[: nkpt * nip * sb].view(nkpt, nip, sb)
-                ops.gram_conjb(xip, f_k[:, s0:s0 + sb, :], out=fxt)
+                with ops.timed("fx_gemm"):
+                    ops.gram_conjb(xip, f_k[:, s0:s0 + sb, :], out=fxt)
                 if fit == "gelsy":
                     yv = y_blk[: nq * nip * sb].view(nq, nip, sb)
-                    ops.ktransform_rows(fxt, nip * sb, sb, yv, nip * sb, sb, 0, nip, sb, kmesh, uax_h,
-                                        conj2=0, qslot=qslot, diag=diag[2:4])                               # :79-85
+                    with ops.timed("ktransform"):
+                        ops.ktransform_rows(fxt, nip * sb, sb, yv, nip * sb, sb, 0, nip, sb, kmesh, uax_h,
+                                            conj2=0, qslot=qslot, diag=diag[2:4])                           # :79-85
                     c0 = g0 - g_lo + s0
-                    ops.gemm_hn_strided(q1s, yv, theta[:, :, c0:c0 + sb])     # (Q1 D^-1)^H Y^T  (zunmqr of zgelsy, :108)
+                    with ops.timed("q1_gemm"):
+                        ops.gemm_hn_strided(q1s, yv, theta[:, :, c0:c0 + sb])  # (Q1 D^-1)^H Y^T  (zunmqr of zgelsy, :108)
                 else:
-                    ops.ktransform_rows(fxt, nip * sb, sb, theta, nipP * ncol, ncol, g0 - g_lo + s0, nip, sb, kmesh,
-                                        uax_h, conj2=0, qslot=qslot, rowmap=rowmap, rowmap_sq=nip, diag=diag[2:4])   # :79-85
+                    with ops.timed("ktransform"):
+                        ops.ktransform_rows(fxt, nip * sb, sb, theta, nipP * ncol, ncol, g0 - g_lo + s0, nip, sb, kmesh,
+                                            uax_h, conj2=0, qslot=qslot, rowmap=rowmap, rowmap_sq=nip, diag=diag[2:4])   # :79-85
         else:
             if fx_k is None or fx_k.numel() != nkpt * blk * nip:
                 fx_k = torch.empty((nkpt * blk * nip,), dtype=torch.complex128, device=dev)
@@ -349,12 +354,14 @@ def build(df_obj):
         # Theta = E Theta~ is never formed: W_q = E (Theta~ K Theta~^H) E^H with orthonormal E
         lfwd = lfwd_g.result()
         del lfwd_g, q1s
-        ops.trsm_sweep(lfwd, theta, nact=rmax, backward=False, ng=ncol)
+        with ops.timed("sweep"):
+            ops.trsm_sweep(lfwd, theta, nact=rmax, backward=False, ng=ncol)
         del lfwd
     else:
         lfwd, ubwd = lfwd_g.result(), ubwd_g.result()
         del lfwd_g, ubwd_g
-        ops.trsm_sweeps(lfwd, ubwd, theta, nact=rmax)     # rows at positions >= max rank are zero and stay zero
+        with ops.timed("sweep"):
+            ops.trsm_sweeps(lfwd, ubwd, theta, nact=rmax)     # rows at positions >= max rank are zero and stay zero
         del lfwd, ubwd
     mark("fit")
     if getattr(df_obj, "keep_theta", False):
@@ -383,7 +390,8 @@ def build(df_obj):
         for s, q in enumerate(qind):                                              # :97
             ops.phase_table(coord_d, vk[q], fq_d)                                 # :99
             ops.coulomb_weights(bvec, kscaled[q], mesh, vol, wgt_d)               # :114-115
-            ops.dft3d_p2p(peerbuf.ptrs, ncol, s * nipP + v_lo, work, v_cnt, mesh, pre=fq_d, post=wgt_d)
+            with ops.timed("fft"):
+                ops.dft3d_p2p(peerbuf.ptrs, ncol, s * nipP + v_lo, work, v_cnt, mesh, pre=fq_d, post=wgt_d)
         peerbuf.barrier()                                    # all scatters have landed
         del work
         mark("fft")
@@ -397,22 +405,26 @@ def build(df_obj):
         for s, q in enumerate(qind):                                              # :97
             ops.phase_table(coord_d, vk[q], fq_d)                                 # :99   fq = exp(-i r.q)
             ops.coulomb_weights(bvec, kscaled[q], mesh, vol, wgt_d)               # :114-115 sqrt(coulG vol)/ng
-            ops.fft3d(vecs[s], mesh, pre=fq_d, post=wgt_d, nvec=nv, ldv=ldv)      # :113-115
+            with ops.timed("fft"):
+                ops.fft3d(vecs[s], mesh, pre=fq_d, post=wgt_d, nvec=nv, ldv=ldv)  # :113-115
         mark("fft")
         theta = sharding.to_column_layout(vecs, comm)            # [nq][nipP][ncol]
         del vecs
     if fit == "gelsy":
         wt = torch.zeros((nq, nipP, nipP), dtype=torch.complex128, device=dev)
-        ops.herk_strided(theta, ncol, nipP * ncol, rmax, ncol, 1.0, None, 0, wt, nipP, nipP * nipP, nq)      # :121
+        with ops.timed("herk"):
+            ops.herk_strided(theta, ncol, nipP * ncol, rmax, ncol, 1.0, None, 0, wt, nipP, nipP * nipP, nq)  # :121
         sharding.allreduce_sum_(wt, comm)
         eh = ehg.result()
         del ehg
-        wslot = ops.hermitize(ops.gemm_hn(eh, ops.gemm_nn(wt, eh)))        # W_q = E W~ E^H
+        with ops.timed("expand_w"):
+            wslot = ops.hermitize(ops.gemm_hn(eh, ops.gemm_nn(wt, eh)))    # W_q = E W~ E^H
         del wt, eh
     else:
         wslot = torch.zeros((nq, nip, nip), dtype=torch.complex128, device=dev)
         nrow = min(nip, rmax)
-        ops.herk_strided(theta, ncol, nipP * ncol, nrow, ncol, 1.0, piv_q, nip, wslot, nip, nip * nip, nq)   # :121
+        with ops.timed("herk"):
+            ops.herk_strided(theta, ncol, nipP * ncol, nrow, ncol, 1.0, piv_q, nip, wslot, nip, nip * nip, nq)   # :121
         sharding.allreduce_sum_(wslot, comm)
     wq = torch.empty((nkpt, nip, nip), dtype=torch.complex128, device=dev)
     for s, q in enumerate(qind):

@@ -31,6 +31,23 @@ def _chk(t, dtype):
     assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.dtype, t.is_contiguous())
 
 
+class _Timed:
+    def __init__(self, ops, name):
+        self.ops, self.name = ops, name
+
+    def __enter__(self):
+        if self.ops.kernel_events is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.ops.kernel_events is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.ops.kernel_events.setdefault(self.name, []).append((self.e0, e1))
+        return False
+
+
 class IsdfOps:
     def __init__(self, device=0):
         self.device = torch.device("cuda", device)
@@ -39,6 +56,17 @@ class IsdfOps:
         self.lib = self.handle.lib
         self.h = self.handle.h
         self.launches = 0  # kernels launched through this object (bench.py's gpu_launches)
+        self.kernel_events = None   # name -> [(start, stop)] CUDA event pairs when per-kernel timing is on
+
+    def timed(self, name):
+        """Context manager: CUDA-event bracket around one kernel (group) on the current stream, accumulated per name
+        when `kernel_events` is a dict (bench.py's per-kernel roofline); free otherwise."""
+        return _Timed(self, name)
+
+    def kernel_ms(self):
+        """Sum of the recorded brackets per name (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in (self.kernel_events or {}).items()}
 
     # ---- K1: selection Gram  (fftisdf.py:376-379) --------------------------------------
     def select_gram(self, x0):
@@ -303,8 +331,10 @@ class IsdfOps:
         _chk(a_q, c128)
         w = torch.empty_like(a_q)
         self.conj_copy(a_q, w)                    # column-major working copy: w[c][i] = A[i][c] = conj(A[c][i])
-        vt, tau, piv, pos = self.qrcp(w)
-        rank = self.gelsy_rank(w, piv, rcond)
+        with self.timed("qrcp"):
+            vt, tau, piv, pos = self.qrcp(w)
+        with self.timed("gelsy_rank"):
+            rank = self.gelsy_rank(w, piv, rcond)
         return dict(w=w, vt=vt, tau=tau, piv=piv, pos=pos, rank=rank)
 
     def gelsy_operators(self, st, rP):

@@ -22,6 +22,23 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    # seconds are the headline (lower is better); the value is the extrapolated build time of the fixed sample
+    assert d["metric"] == "isdf_build_seconds" and d["unit"] == "s" and d["higher_is_better"] is False
+    assert d["cpu_baseline"]["value"] == d["cpu_baseline"]["extrapolated_build_s"] == d["value"]
+    for k in ("workload", "nk", "nao", "n0", "nip", "ng", "mesh", "kmesh", "c0", "fit"):   # same keys as the device arm
+        assert k in d["config"], k
+
+
+def test_reference_arm_value_does_not_depend_on_steps():
+    """The sample is fixed: --steps / --warmup change how often it is repeated, not what is measured."""
+    sys.path.insert(0, ROOT)
+    import bench
+    cell, kpts, w = bench.make_workload("tiny")
+    tables = bench.ao_tables(cell, kpts, w["m0"])
+    a = bench.cpu_sample(cell, kpts, w, tables)
+    b = bench.cpu_sample(cell, kpts, w, tables)
+    assert a["sample"].split(":")[0] == b["sample"].split(":")[0]          # identical sample definition
+    assert a["nip"] == b["nip"] and abs(a["value"] - a["extrapolated_build_s"]) == 0.0
 
 
 def test_flop_model_matches_oracle_model():

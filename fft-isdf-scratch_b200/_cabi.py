@@ -65,6 +65,9 @@ SIGNATURES = {
     "isdf_trsm_sweeps": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_long, c_int, c_void_p],
     "isdf_ktransform_square": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_long, c_long, c_int,
                                c_int, P_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_long, c_void_p, c_void_p],
+    "isdf_ktransform_ex": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_long, c_long, c_int,
+                           c_int, P_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p,
+                           c_long, c_long, c_double, c_void_p],
     "isdf_fft3d_batched": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_long, c_void_p],
     "isdf_fft_release_plans": [c_void_p],
     "isdf_dft3d_dmma": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_void_p],

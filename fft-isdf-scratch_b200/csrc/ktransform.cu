@@ -32,6 +32,10 @@ struct KtParams {
   const int* qslot;             // [nk] output slot per q, -1 = skip (may be null = identity)
   const int* rowmap; long rowmap_sq;  // [nslot][ni] output row per i, -1 = drop (may be null)
   double* diag;                 // diag[0] = max |Im s|, diag[1] = max |Re s|
+  // mode 0: y = Re(s)^2 (metric / right-hand side).  mode 1: y = scale * Re(s) * table[R][g][i] (exchange:
+  // vs = ws * rhos^T, fftisdf.py:215-223).  mode 2: write scale * Re(s) as a REAL table out[R][g][i] and stop
+  // (ws = Re(phase @ wq) sqrt(nk), fftisdf.py:205-207).
+  int mode; const double* table; long tab_sk; long tab_sg; double scale;
 };
 
 // one pass of N-point DFTs along one k-mesh axis, in place in shared memory.
@@ -122,7 +126,22 @@ __global__ void __launch_bounds__(KT_THREADS) ktransform_square_kernel(KtParams 
     cplx v = s[w];
     mx_im = fmax(mx_im, fabs(v.y));
     mx_re = fmax(mx_re, fabs(v.x));
-    s[w] = make_double2(v.x * v.x, 0.0);
+    if (p.mode == 0) {
+      s[w] = make_double2(v.x * v.x, 0.0);
+    } else {
+      const int R = w / EP, r = w - R * EP;
+      const int gg = r / (KT_IT + 1), ii = r - gg * (KT_IT + 1);
+      double y = 0.0;
+      if (gg < gcnt && ii < icnt) {
+        if (p.mode == 1) {
+          y = p.scale * v.x * p.table[(long)R * p.tab_sk + (long)(g0 + gg) * p.tab_sg + (i0 + ii)];
+        } else {   // mode 2: real output table, no second transform
+          reinterpret_cast<double*>(p.out)[(long)R * p.out_sq + (p.out_g0 + g0 + gg) * p.out_sg + (long)(i0 + ii) * p.out_si] =
+              p.scale * v.x;
+        }
+      }
+      s[w] = make_double2(y, 0.0);
+    }
   }
   if (p.diag != nullptr) {
 #pragma unroll
@@ -136,6 +155,7 @@ __global__ void __launch_bounds__(KT_THREADS) ktransform_square_kernel(KtParams 
     }
   }
   __syncthreads();
+  if (p.mode == 2) return;
 
   // ---- second transform
   if (p.conj2) {
@@ -171,11 +191,27 @@ __global__ void __launch_bounds__(KT_THREADS) ktransform_square_kernel(KtParams 
 
 using namespace isdf;
 
+extern "C" int isdf_ktransform_ex(void* hv, const void* in, long in_sk, long in_sg, void* out, long out_sq,
+                                  long out_sg, long out_si, long out_g0, int ng, int ni, const int* kmesh,
+                                  const void* uaxes_dev, int conj2, int out_g_fast, const int* qslot_dev,
+                                  const int* rowmap_dev, long rowmap_sq, double* diag_dev, int mode,
+                                  const double* table, long tab_sk, long tab_sg, double scale, void* stream);
+
 extern "C" int isdf_ktransform_square(void* hv, const void* in, long in_sk, long in_sg, void* out, long out_sq,
                                       long out_sg, long out_si, long out_g0, int ng, int ni, const int* kmesh,
                                       const void* uaxes_dev, int conj2, int out_g_fast, const int* qslot_dev,
                                       const int* rowmap_dev, long rowmap_sq, double* diag_dev, void* stream) {
+  return isdf_ktransform_ex(hv, in, in_sk, in_sg, out, out_sq, out_sg, out_si, out_g0, ng, ni, kmesh, uaxes_dev, conj2,
+                            out_g_fast, qslot_dev, rowmap_dev, rowmap_sq, diag_dev, 0, nullptr, 0, 0, 1.0, stream);
+}
+
+extern "C" int isdf_ktransform_ex(void* hv, const void* in, long in_sk, long in_sg, void* out, long out_sq,
+                                  long out_sg, long out_si, long out_g0, int ng, int ni, const int* kmesh,
+                                  const void* uaxes_dev, int conj2, int out_g_fast, const int* qslot_dev,
+                                  const int* rowmap_dev, long rowmap_sq, double* diag_dev, int mode,
+                                  const double* table, long tab_sk, long tab_sg, double scale, void* stream) {
   Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, mode >= 0 && mode <= 2 && (mode != 1 || table != nullptr), "mode/table");
   ISDF_CHECK_ARG(h, in && out && kmesh && uaxes_dev, "null pointer");
   ISDF_CHECK_ARG(h, kmesh[0] >= 1 && kmesh[1] >= 1 && kmesh[2] >= 1, "kmesh");
   ISDF_CHECK_ARG(h, kmesh[0] <= KT_NMAX && kmesh[1] <= KT_NMAX && kmesh[2] <= KT_NMAX, "kmesh axis > 8 unsupported");
@@ -193,6 +229,7 @@ extern "C" int isdf_ktransform_square(void* hv, const void* in, long in_sk, long
   p.gt = gt; p.conj2 = conj2; p.out_g_fast = out_g_fast;
   p.uax = (const cplx*)uaxes_dev; p.qslot = qslot_dev; p.rowmap = rowmap_dev; p.rowmap_sq = rowmap_sq;
   p.diag = diag_dev;
+  p.mode = mode; p.table = table; p.tab_sk = tab_sk; p.tab_sg = tab_sg; p.scale = scale;
   const size_t smem = bytes(gt);
   ISDF_CUDA(h, cudaFuncSetAttribute(ktransform_square_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((ni + KT_IT - 1) / KT_IT, (ng + gt - 1) / gt);

@@ -290,6 +290,9 @@ extern "C" int isdf_ktransform_rows_ex(void* hv, const void* in, long in_sk, lon
   KT_CASE(2, 3, 1) KT_CASE(3, 1, 2) KT_CASE(3, 2, 1) KT_CASE(1, 1, 4) KT_CASE(1, 4, 1) KT_CASE(4, 1, 1)
   KT_CASE(2, 2, 4) KT_CASE(2, 4, 2) KT_CASE(4, 2, 2) KT_CASE(1, 4, 4) KT_CASE(4, 1, 4) KT_CASE(4, 4, 1)
   KT_CASE(2, 4, 4) KT_CASE(4, 2, 4) KT_CASE(4, 4, 2)
+  KT_CASE(1, 2, 4) KT_CASE(1, 4, 2) KT_CASE(2, 1, 4) KT_CASE(2, 4, 1) KT_CASE(4, 1, 2) KT_CASE(4, 2, 1)
+  KT_CASE(1, 3, 4) KT_CASE(1, 4, 3) KT_CASE(3, 1, 4) KT_CASE(3, 4, 1) KT_CASE(4, 1, 3) KT_CASE(4, 3, 1)
+  KT_CASE(2, 3, 4) KT_CASE(2, 4, 3) KT_CASE(3, 2, 4) KT_CASE(3, 4, 2) KT_CASE(4, 2, 3) KT_CASE(4, 3, 2)
 #define KT_SPLIT(a, b, c, sa) \
   if (n1 == a && n2 == b && n3 == c) { e = launch_split<a, b, c, sa>(p, st); hit = true; }
   KT_SPLIT(4, 4, 4, 0) KT_SPLIT(3, 4, 4, 1) KT_SPLIT(4, 3, 4, 0) KT_SPLIT(4, 4, 3, 0) KT_SPLIT(4, 3, 3, 0)

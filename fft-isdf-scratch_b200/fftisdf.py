@@ -452,70 +452,36 @@ def build(df_obj):
 
 
 def get_j_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=None, exxdiv=None):
-    """fftisdf.py:133-171 (host numpy on the small [nk,nip,nao] / [nip,nip] outputs of the build)."""
+    """fftisdf.py:133-171 on the device outputs of the build (no host arithmetic)."""
     assert exxdiv is None
     kpts = numpy.asarray(kpts)
     dm_kpts = numpy.asarray(dm_kpts, order="C")
     nkpt = len(kpts)
     nao = dm_kpts.shape[-1]
     dms = dm_kpts.reshape(-1, nkpt, nao, nao)
-    nset = dms.shape[0]
-    assert df_obj._x is not None and df_obj._w0 is not None
-    nip = df_obj._x.shape[1]
-    assert df_obj._x.shape == (nkpt, nip, nao)
-    assert df_obj._w0.shape == (nip, nip)
+    assert getattr(df_obj, "_x_dev", None) is not None and df_obj._wq_dev is not None, "call build() first"
+    nip = df_obj._x_dev.shape[1]
+    assert tuple(df_obj._x_dev.shape) == (nkpt, nip, nao)
     assert kpts_band is None, "kpts_band is not supported (fftisdf.py:164)"
-    if _jk_device_ok(df_obj):
-        vj_kpts = get_j_kpts_device(df_obj, dms)
-        if abs(kpts).max() < 1e-9:
-            vj_kpts = vj_kpts.real
-        return vj_kpts.reshape(dm_kpts.shape)
-    rho = numpy.einsum("kIm,kIn,xkmn->xI", df_obj._x, df_obj._x.conj(), dms, optimize=True)
-    rho *= 1.0 / nkpt
-    v = numpy.einsum("IJ,xJ->xI", df_obj._w0, rho, optimize=True)
-    vj_kpts = numpy.einsum("kIm,kIn,xI->xkmn", df_obj._x.conj(), df_obj._x, v, optimize=True)
-    assert vj_kpts.shape == (nset, nkpt, nao, nao)
+    vj_kpts = get_j_kpts_device(df_obj, dms)
     if abs(kpts).max() < 1e-9:
         vj_kpts = vj_kpts.real
     return vj_kpts.reshape(dm_kpts.shape)
 
 
 def get_k_kpts(df_obj, dm_kpts, hermi=1, kpts=numpy.zeros((1, 3)), kpts_band=None, exxdiv=None):
-    """fftisdf.py:173-228."""
+    """fftisdf.py:173-228 on the device outputs of the build (no host arithmetic)."""
     assert exxdiv is None
     assert kpts_band is None, "kpts_band is not supported (fftisdf.py:194)"
-    pcell = df_obj.cell
-    kmesh = df_obj.kmesh
-    phase = pbc_tools.get_phase(numpy.asarray(pcell.lattice_vectors()), df_obj.kpts, kmesh)
     dm_kpts = numpy.asarray(dm_kpts, order="C")
     nkpt = len(numpy.asarray(kpts))
     nao = dm_kpts.shape[-1]
     dms = dm_kpts.reshape(-1, nkpt, nao, nao)
-    nset = dms.shape[0]
-    nip = df_obj._x.shape[1]
-    assert df_obj._x.shape == (nkpt, nip, nao)
-    assert df_obj._wq.shape == (nkpt, nip, nip)
-    if _jk_device_ok(df_obj):
-        return get_k_kpts_device(df_obj, dms).reshape(dm_kpts.shape)
-    ws = phase @ df_obj._wq.reshape(nkpt, -1)
-    ws = ws.reshape(nkpt, nip, nip)
-    ws = ws.real * numpy.sqrt(nkpt)
-    vk_kpts = []
-    for dm in dms:
-        rhok = numpy.asarray([x @ d @ x.conj().T for x, d in zip(df_obj._x, dm)]) / nkpt
-        rhos = phase @ rhok.reshape(nkpt, -1)
-        assert abs(rhos.imag).max() < 1e-10
-        rhos = rhos.real.reshape(nkpt, nip, nip)
-        vs = ws * rhos.transpose(0, 2, 1)
-        vk = (phase.T @ vs.reshape(nkpt, -1)).reshape(nkpt, nip, nip)
-        vk_kpts.append([x.conj().T @ v @ x for x, v in zip(df_obj._x, vk)])
-    vk_kpts = numpy.asarray(vk_kpts).reshape(nset, nkpt, nao, nao)
-    return vk_kpts.reshape(dm_kpts.shape)
-
-
-def _jk_device_ok(df_obj):
-    return (getattr(df_obj, "jk_on_device", True) and getattr(df_obj, "_x_dev", None) is not None
-            and max(df_obj.kmesh) <= 4)
+    assert getattr(df_obj, "_x_dev", None) is not None and df_obj._wq_dev is not None, "call build() first"
+    nip = df_obj._x_dev.shape[1]
+    assert tuple(df_obj._x_dev.shape) == (nkpt, nip, nao)
+    assert tuple(df_obj._wq_dev.shape) == (nkpt, nip, nip)
+    return get_k_kpts_device(df_obj, dms).reshape(dm_kpts.shape)
 
 
 def get_j_kpts_device(df_obj, dms):
@@ -535,27 +501,35 @@ def get_j_kpts_device(df_obj, dms):
     return numpy.asarray(out)
 
 
+def _ktrans_jk(ops, kmesh, vin, out, mode, table=None, scale=1.0, diag=None):
+    """k<->R transform of [nk, nip, nip] data for the exchange build: register kernel for small k-meshes, the
+    shared-memory kernel otherwise (axes <= 8)."""
+    nk, nip, _ = vin.shape
+    ok = ops.ktransform_rows_ex(vin, nip * nip, nip, out, nip * nip, nip, 0, nip, nip, kmesh,
+                                ops.pack_uaxes_host(kmesh), 0, mode=mode, table=table, tab_sk=nip * nip, tab_sr=nip,
+                                scale=scale, diag=diag)
+    if not ok:
+        ops.ktransform_general(vin, nip * nip, nip, out, nip * nip, nip, 1, nip, nip, kmesh, ops.pack_uaxes(kmesh), 0,
+                               mode=mode, table=table, tab_sk=nip * nip, tab_sg=nip, scale=scale, diag=diag)
+
+
 def get_k_kpts_device(df_obj, dms):
-    """fftisdf.py:204-227 on the device (k<->R transforms with the register k-transform kernels)."""
+    """fftisdf.py:204-227 on the device (k<->R transforms with the k-transform kernels)."""
     ops = df_obj._ops
     x = df_obj._x_dev
     wq = df_obj._wq_dev
     nk, nip, nao = x.shape
     kmesh = df_obj.kmesh
-    uax_h = ops.pack_uaxes_host(kmesh)
     diag = torch.zeros(2, dtype=torch.float64, device=ops.device)
     ws = torch.empty((nk, nip, nip), dtype=torch.float64, device=ops.device)
-    ok = ops.ktransform_rows_ex(wq, nip * nip, nip, ws, nip * nip, nip, 0, nip, nip, kmesh, uax_h, 0, mode=2,
-                                scale=float(numpy.sqrt(nk)))              # :205-207 ws = Re(phase @ wq) sqrt(nk)
-    assert ok
+    _ktrans_jk(ops, kmesh, wq, ws, 2, scale=float(numpy.sqrt(nk)))       # :205-207 ws = Re(phase @ wq) sqrt(nk)
     out = []
     for dm in dms:
         d = torch.from_numpy(numpy.ascontiguousarray(dm, dtype=numpy.complex128)).to(ops.device)
         y = ops.gemm_nn(x, d)                                             # Y_k = X_k D_k
         g = ops.gram_conja(x, y)                                          # g[k][I][J] = rhok[k][J][I] * nk   (:211)
         vk_ip = torch.empty((nk, nip, nip), dtype=torch.complex128, device=ops.device)
-        ops.ktransform_rows_ex(g, nip * nip, nip, vk_ip, nip * nip, nip, 0, nip, nip, kmesh, uax_h, 0, mode=1,
-                               table=ws, tab_sk=nip * nip, tab_sr=nip, scale=1.0 / nk, diag=diag)   # :212-223
+        _ktrans_jk(ops, kmesh, g, vk_ip, 1, table=ws, scale=1.0 / nk, diag=diag)   # :212-223
         z = ops.gemm_nn(vk_ip, x)                                         # vk X_k
         out.append(ops.gemm_hn(x, z).cpu().numpy())                       # :225  X_k^H vk X_k
     dd = diag.cpu().numpy()

@@ -222,6 +222,16 @@ class IsdfOps:
             "isdf_ktransform_square")
         self.launches += 1
 
+    def ktransform_general(self, vin, in_sk, in_sg, out, out_sq, out_sg, out_si, ng, ni, kmesh, uaxes, conj2, mode,
+                           table=None, tab_sk=0, tab_sg=0, scale=1.0, diag=None):
+        """Shared-memory k-transform (axes <= 8) with the exchange modes of ktransform_rows_ex."""
+        km = (C.c_int * 3)(*[int(x) for x in kmesh])
+        self.handle.check(self.lib.isdf_ktransform_ex(
+            self.h, _ptr(vin), in_sk, in_sg, _ptr(out), out_sq, out_sg, out_si, 0, ng, ni, km, _ptr(uaxes),
+            int(conj2), 0, None, None, 0, _ptr(diag), int(mode), _ptr(table), tab_sk, tab_sg, float(scale),
+            _stream()), "isdf_ktransform_ex")
+        self.launches += 1
+
     # ---- K5: triangular sweeps ----------------------------------------------------------------
     def trsm_prepare(self, u, piv, rank, nP):
         batch, ldu, n = u.shape

@@ -86,6 +86,15 @@ int isdf_ktransform_square(void* handle, const void* in, long in_sk, long in_sg,
                            int out_g_fast, const int* qslot, const int* rowmap, long rowmap_sq, double* diag,
                            void* stream);
 
+/* General form of isdf_ktransform_square (any k-mesh with axes <= 8), same modes as isdf_ktransform_rows_ex below:
+ * mode 0 = square; mode 1 = multiply scale*Re(s) by the real R-space table[R*tab_sk + g*tab_sg + i] before the second
+ * transform (fftisdf.py:215-223); mode 2 = write scale*Re(s) as a real table (doubles, strides in doubles) and stop
+ * (fftisdf.py:205-207). */
+int isdf_ktransform_ex(void* handle, const void* in, long in_sk, long in_sg, void* out, long out_sq, long out_sg,
+                       long out_si, long out_g0, int ng, int ni, const int* kmesh, const void* uaxes, int conj2,
+                       int out_g_fast, const int* qslot, const int* rowmap, long rowmap_sq, double* diag, int mode,
+                       const double* table, long tab_sk, long tab_sg, double scale, void* stream);
+
 /* Register-resident variant of isdf_ktransform_square for small k-meshes (every axis <= 4, nk <= 32):
  * in[k*in_sk + r*in_sr + c] (c contiguous) -> out[slot*out_sq + row*out_sr + out_c0 + c], row = rowmap[slot][r].
  * uaxes is a HOST pointer here (3 x [8][8] c128, copied to constant memory).  Returns -2 without launching

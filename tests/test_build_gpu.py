@@ -304,16 +304,36 @@ def test_exact_isdf_reproduces_eris(kmesh):
 
 @pytest.mark.parametrize("name", ["k321_spd", "k231_odd", "k333_odd", "k434_odd", "gamma_s"])
 def test_device_jk_equals_host_jk_and_reference(name):
-    """get_j_kpts / get_k_kpts on the device == the numpy statement of fftisdf.py:133-228 == golden."""
+    """get_j_kpts / get_k_kpts on the device == the oracle's numpy statement of fftisdf.py:133-228 applied
+    to the device's own (X, W_q) == golden."""
     g, df = run_golden(name)
     dm2 = np.stack([g["dm"], g["dm"].conj().transpose(0, 2, 1) * 0.5])      # two density-matrix sets
-    df.jk_on_device = True
     vj_d, vk_d = df.get_jk(dm2, kpts=g["kpts"])
-    df.jk_on_device = False
-    vj_h, vk_h = df.get_jk(dm2, kpts=g["kpts"])
+    ph = H.get_phase(g["a"], g["kpts"], g["kmesh"].tolist())
+    vj_h = O.get_j_kpts(df._x, df._w0, dm2)
+    vk_h = O.get_k_kpts(df._x, df._wq, dm2, ph)
     assert rel(vj_d, vj_h) < 1e-12 and rel(vk_d, vk_h) < 1e-12
     assert rel(vj_d[0], g["vj"].reshape(vj_d[0].shape)) < 1e-10
     assert rel(vk_d[0], g["vk"].reshape(vk_d[0].shape)) < 1e-10
+
+
+@pytest.mark.parametrize("kmesh", [[1, 2, 4], [4, 3, 1], [2, 3, 4], [3, 4, 2], [1, 5, 2], [6, 1, 1]])
+def test_jk_on_every_supported_kmesh_shape(kmesh):
+    """k-meshes whose register k-transform instantiations were missing in round 1 (permutations of (1,2,4), (1,3,4),
+    (2,3,4): get_jk hit an assert) and meshes with an axis > 4 (shared-memory kernel, exchange modes added)."""
+    import fft_isdf_scratch_b200 as pk
+    cell = pk.random_cubic_cell(8, 5, seed=90 + sum(kmesh), L=6.0, ltypes="sp")
+    df, out = _run_synth(cell, kmesh, [5, 5, 5], 2.0)
+    nk, nao = len(df.kpts), cell.nao_nr()
+    rng = np.random.default_rng(5)
+    dm = rng.standard_normal((nk, nao, nao)) + 1j * rng.standard_normal((nk, nao, nao))
+    dm = dm + dm.conj().transpose(0, 2, 1)
+    tr = pk.pbc_tools.time_reversal_partner(kmesh)
+    dm = 0.5 * (dm + dm[tr].conj())
+    vj, vk = df.get_jk(dm, kpts=df.kpts)
+    ph = H.get_phase(cell.a, df.kpts, kmesh)
+    assert rel(vj, O.get_j_kpts(df._x, df._w0, dm[None])[0]) < 1e-12
+    assert rel(vk, O.get_k_kpts(df._x, df._wq, dm[None], ph)[0]) < 1e-12
 
 
 def _run_synth(cell, kmesh, m0, c0, **attrs):
@@ -332,7 +352,7 @@ def _run_synth(cell, kmesh, m0, c0, **attrs):
 
 
 def test_fallback_kernels_large_kmesh_axis_and_long_fft_axis():
-    """k-mesh axis 5 (shared-memory k-transform, numpy J/K statement) and a 50-point FFT axis (Stockham kernel
+    """k-mesh axis 5 (shared-memory k-transform, also for J/K) and a 50-point FFT axis (Stockham kernel
     instead of the tensor-core DFT) through the same build(): same parity bar as the fast paths."""
     import fft_isdf_scratch_b200 as pk
     cell = pk.random_cubic_cell(12, 10, seed=52, L=8.0, ltypes="spd")
@@ -368,8 +388,9 @@ def test_all_parent_points_selected_and_single_block():
     w = df._wq[0]
     assert np.isfinite(w).all() and np.abs(w - w.conj().T).max() == 0.0
     vj, vk = df.get_jk(np.eye(3)[None], kpts=df.kpts)          # real-dtype density matrix (common at Gamma)
-    df.jk_on_device = False
-    vj_h, vk_h = df.get_jk(np.eye(3)[None], kpts=df.kpts)
+    dmc = np.eye(3)[None, None].astype(complex)
+    vj_h = O.get_j_kpts(df._x, df._w0, dmc)[0]
+    vk_h = O.get_k_kpts(df._x, df._wq, dmc, H.get_phase(cell.a, df.kpts, [1, 1, 1]))[0]
     assert np.isfinite(vj).all() and np.isfinite(vk).all()
     assert rel(vj, vj_h) < 1e-10 and rel(vk, vk_h) < 1e-10
 

@@ -22,8 +22,8 @@
 //       auxv = -tau V^H v_k and the pivot row of V;
 //   S2  cluster barrier -- every CTA computes, for its live columns, F[c,t] = tau a_c^H v_k + F[c,:t] auxv
 //       (warp per column, coalesced), the pivot-row update R[k,c] and the norm downdate.
-// A panel ends after nb steps or as soon as a column asks for its norm to be recomputed; the owner CTAs then
-// apply the deferred rank-nb update to their columns.
+// A panel ends after nb steps; the owner CTAs then apply the deferred rank-nb update to their columns.  (zlaqps also
+// ends it when a column asks for its norm to be recomputed; here that column is brought up to date on the fly.)
 #include <float.h>
 #include <cooperative_groups.h>
 #include "gemm_c128.cuh"
@@ -41,11 +41,19 @@ constexpr int QR_RT_MIN = 64;          // rows per trailing-update tile (lower b
 
 struct QrCand { double v; int pos; int idx; int flag; };
 struct QrBcast { cplx aux[QR_NB_MAX]; cplx vrow[QR_NB_MAX]; cplx tau; };
+struct QrPart { cplx dots[QR_NB_MAX]; cplx ak; double nrm2; double pad; };
 
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
+}
+
+// Fire-and-forget L2 prefetch of w[i0..n) by one warp (128-byte lines = 8 complex): turns the DRAM latency of the
+// demand loads that follow into L2 latency without holding registers for the bytes in flight.
+__device__ __forceinline__ void warp_prefetch_l2(const cplx* w, int i0, int n, int lane) {
+  for (int i = (i0 & ~7) + lane * 8; i < n; i += 256)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(w + i));
 }
 
 // 2-norm of w[i0..n) by one warp
@@ -81,7 +89,10 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
   int* pos = reinterpret_cast<int*>(vn2 + ncc);                   // [ncc]
   int* mark = pos + ncc;                                          // [ncc]
   __shared__ QrCand cand[2][QR_CS_MAX];
-  __shared__ QrBcast bc[2];
+  __shared__ QrBcast bc[1];
+  __shared__ QrPart part[2][QR_CS_MAX];
+  __shared__ cplx fp[QR_NB_MAX];
+  __shared__ cplx mydots[QR_NB_MAX];
   __shared__ double red_v[QR_NW];
   __shared__ int red_pos[QR_NW], red_idx[QR_NW], red_flag[QR_NW];
   __shared__ double s_scal[6];     // beta, tau.re, tau.im, scale.re, scale.im, spare
@@ -157,7 +168,7 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
         anyflag |= cand[par][r].flag;
         if (oi >= 0 && (ov > dp || (ov == dp && op < ppos))) { dp = ov; ppos = op; p = oi; }
       }
-      if (anyflag && t > 0) break;      // zlaqps: a column needs its norm recomputed -> close the panel first
+      (void)anyflag;
       // ---- positions: column p takes position k, the column that sat at k moves to p's old position
 #pragma unroll
       for (int j = 0; j < QR_NCOLT; ++j) {
@@ -168,87 +179,122 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
         }
       }
       const int owner = p / ncc;
-      if (crank == owner) {
-        const int lp = p - c_lo;
-        const cplx* Wp = W + (long)p * n;
-        // pending panel reflectors onto the pivot column:  a_p -= sum_tt v_tt conj(F[p][tt])   (rows >= k)
-        for (int i = k + tid; i < n; i += QR_THREADS) {
-          cplx a = Wp[i];
-          for (int tt = 0; tt < t; ++tt) {
-            const cplx vv = __ldcg(V + (long)(j0 + tt) * n + i);
-            const cplx f = Ft[(long)tt * ncc + lp];
-            a.x -= vv.x * f.x + vv.y * f.y;      // vv * conj(f)
-            a.y -= vv.y * f.x - vv.x * f.y;
-          }
-          vbuf[i] = a;
-        }
-        __syncthreads();
-        // zlarfg
-        double ss = 0.0;
-        for (int i = k + 1 + tid; i < n; i += QR_THREADS) { const cplx a = vbuf[i]; ss += a.x * a.x + a.y * a.y; }
-        ss = warp_sum(ss);
-        if (lane == 0) red_v[warp] = ss;
-        __syncthreads();
-        if (tid == 0) {
-          double tot = 0.0;
-          for (int w = 0; w < QR_NW; ++w) tot += red_v[w];
-          const cplx alpha = vbuf[k];
-          double beta, tr, ti, sr, si;
-          if (tot == 0.0 && alpha.y == 0.0) {
-            beta = alpha.x; tr = 0.0; ti = 0.0; sr = 0.0; si = 0.0;
-          } else {
-            beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + tot), alpha.x);
-            tr = (beta - alpha.x) / beta; ti = -alpha.y / beta;
-            const double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;   // 1 / (alpha - beta)
-            sr = dr / den; si = -di / den;
-          }
-          s_scal[0] = beta; s_scal[1] = tr; s_scal[2] = ti; s_scal[3] = sr; s_scal[4] = si;
-        }
-        __syncthreads();
-        const double beta = s_scal[0];
-        const cplx tau = make_double2(s_scal[1], s_scal[2]);
-        const cplx scal = make_double2(s_scal[3], s_scal[4]);
-        const bool ident = (tau.x == 0.0 && tau.y == 0.0);       // H = I: represented by v = 0
-        for (int i = k + tid; i < n; i += QR_THREADS) {
-          cplx a;
-          if (ident) a = make_double2(0.0, 0.0);
-          else if (i == k) a = make_double2(1.0, 0.0);
-          else a = cmul(vbuf[i], scal);
-          vbuf[i] = a;
-          V[(long)k * n + i] = a;
-        }
-        if (tid == 0) { W[(long)p * n + k] = make_double2(beta, 0.0); tau_out[k] = tau; }
-        __syncthreads();
-        // auxv[tt] = -tau * sum_i conj(v_tt[i]) v_k[i];  vrow[tt] = v_tt[k]
-        for (int tt = warp; tt < t; tt += QR_NW) {
-          const cplx* Vt = V + (long)(j0 + tt) * n;
-          double sr = 0.0, si = 0.0;
-          for (int i = k + lane; i < n; i += 32) {
-            const cplx a = __ldcg(Vt + i), v = vbuf[i];
-            sr += a.x * v.x + a.y * v.y;        // conj(a) * v
-            si += a.x * v.y - a.y * v.x;
-          }
-          sr = warp_sum(sr); si = warp_sum(si);
-          const cplx ax = make_double2(-(tau.x * sr - tau.y * si), -(tau.x * si + tau.y * sr));
-          const cplx vr = __ldcg(Vt + k);
-          if (lane < CS) {
-            QrBcast* remote = cluster.map_shared_rank(bc, lane);
-            remote[par].aux[tt] = ax;
-            remote[par].vrow[tt] = vr;
+      const int lp = p - owner * ncc;
+      // ---- the pivot column, by ALL CTAs of the cluster: CTA r takes the r-th slice of the rows [k, n)
+      //      (one row per thread).  fp = F[p][0..t) comes from the owner's shared memory (DSMEM read).
+      if (tid < t) {
+        const cplx* Fo = cluster.map_shared_rank(Ft, owner);
+        fp[tid] = Fo[(long)tid * ncc + lp];
+      }
+      __syncthreads();
+      const int sl = (n - k + CS - 1) / CS;
+      const int i_lo = k + crank * sl;
+      const int cnt = max(0, min(sl, n - i_lo));
+      double ss = 0.0;
+      for (int r = tid; r < cnt; r += QR_THREADS) {
+        const int my_i = i_lo + r;
+        cplx a = __ldcg(W + (long)p * n + my_i);
+        // a_p -= sum_tt v_tt conj(F[p][tt]); loads in batches of 8 (the column of V is L2-resident, latency-bound)
+        for (int t0 = 0; t0 < t; t0 += 8) {
+          cplx vv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            vv[u] = (t0 + u < t) ? __ldcg(V + (long)(j0 + t0 + u) * n + my_i) : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (t0 + u < t) {
+              const cplx f = fp[t0 + u];
+              a.x -= vv[u].x * f.x + vv[u].y * f.y;      // vv * conj(f)
+              a.y -= vv[u].y * f.x - vv[u].x * f.y;
+            }
           }
         }
-        if (tid < CS) {
-          QrBcast* remote = cluster.map_shared_rank(bc, tid);
-          remote[par].tau = tau;
+        vbuf[r] = a;                                      // slice buffer (the previous reflector is dead by now)
+        if (my_i > k) ss += a.x * a.x + a.y * a.y;
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) red_v[warp] = ss;
+      __syncthreads();
+      // partial dots[tt] = sum_{i in slice, i > k} conj(v_tt[i]) a[i]   (warp per tt)
+      for (int tt = warp; tt < t; tt += QR_NW) {
+        const cplx* Vt = V + (long)(j0 + tt) * n + i_lo;
+        double sr = 0.0, si = 0.0;
+        for (int r = lane; r < cnt; r += 32) {
+          if (i_lo + r > k) {
+            const cplx vv = __ldcg(Vt + r), av = vbuf[r];
+            sr += vv.x * av.x + vv.y * av.y;        // conj(vv) * av
+            si += vv.x * av.y - vv.y * av.x;
+          }
+        }
+        sr = warp_sum(sr); si = warp_sum(si);
+        if (lane == 0) mydots[tt] = make_double2(sr, si);
+      }
+      __syncthreads();
+      // publish {dots[0..t), a_k, |a|^2} into every CTA's table
+      {
+        const int nval = t + 2;
+        for (int e = tid; e < nval * CS; e += QR_THREADS) {
+          const int dst = e / nval, idx = e - dst * nval;
+          QrPart (*remote)[QR_CS_MAX] = cluster.map_shared_rank(part, dst);
+          if (idx < t) remote[par][crank].dots[idx] = mydots[idx];
+          else if (idx == t) remote[par][crank].ak = (crank == 0) ? vbuf[0] : make_double2(0.0, 0.0);
+          else {
+            double tot = 0.0;
+            for (int w = 0; w < QR_NW; ++w) tot += red_v[w];
+            remote[par][crank].nrm2 = tot;
+          }
         }
       }
       cluster.sync();
-      // ---- S2: everyone holds v_k (owner: in vbuf already), tau, auxv, vrow
-      if (crank != owner) {
-        for (int i = k + tid; i < n; i += QR_THREADS) vbuf[i] = __ldcg(V + (long)k * n + i);
+      // ---- every CTA: totals, zlarfg, auxv; scales and stores its slice of v_k
+      if (tid < t) {
+        double sr = 0.0, si = 0.0;
+        for (int r = 0; r < CS; ++r) { sr += part[par][r].dots[tid].x; si += part[par][r].dots[tid].y; }
+        mydots[tid] = make_double2(sr, si);
+      }
+      if (tid == 32) {
+        double tot = 0.0;
+        for (int r = 0; r < CS; ++r) tot += part[par][r].nrm2;
+        const cplx alpha = part[par][0].ak;
+        double beta, tr, ti, sr, si;
+        if (tot == 0.0 && alpha.y == 0.0) {
+          beta = alpha.x; tr = 0.0; ti = 0.0; sr = 0.0; si = 0.0;
+        } else {
+          beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + tot), alpha.x);
+          tr = (beta - alpha.x) / beta; ti = -alpha.y / beta;
+          const double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;   // 1 / (alpha - beta)
+          sr = dr / den; si = -di / den;
+        }
+        s_scal[0] = beta; s_scal[1] = tr; s_scal[2] = ti; s_scal[3] = sr; s_scal[4] = si;
       }
       __syncthreads();
-      const cplx tau = bc[par].tau;
+      const double beta = s_scal[0];
+      const cplx tau = make_double2(s_scal[1], s_scal[2]);
+      const cplx scal = make_double2(s_scal[3], s_scal[4]);
+      const bool ident = (tau.x == 0.0 && tau.y == 0.0);       // H = I: represented by v = 0
+      if (tid < t) {
+        // auxv[tt] = -tau (conj(v_tt[k]) + scale * dots[tt]);  vrow[tt] = v_tt[k]
+        const cplx vr = __ldcg(V + (long)(j0 + tid) * n + k);
+        const cplx sd = cmul(scal, mydots[tid]);
+        const cplx in = ident ? make_double2(0.0, 0.0) : make_double2(vr.x + sd.x, -vr.y + sd.y);
+        bc[0].aux[tid] = make_double2(-(tau.x * in.x - tau.y * in.y), -(tau.x * in.y + tau.y * in.x));
+        bc[0].vrow[tid] = vr;
+      }
+      for (int r = tid; r < cnt; r += QR_THREADS) {
+        const int my_i = i_lo + r;
+        cplx v;
+        if (ident) v = make_double2(0.0, 0.0);
+        else if (my_i == k) v = make_double2(1.0, 0.0);
+        else v = cmul(vbuf[r], scal);
+        V[(long)k * n + my_i] = v;
+      }
+      __syncthreads();    // the slice in vbuf is consumed before the full reflector overwrites it
+      if (crank == owner && tid == 0) { W[(long)p * n + k] = make_double2(beta, 0.0); tau_out[k] = tau; }
+      cluster.sync();
+      // ---- every CTA holds tau, auxv, vrow; the full reflector comes back from global memory (L2)
+      for (int i = k + tid; i < n; i += QR_THREADS) vbuf[i] = __ldcg(V + (long)k * n + i);
+      __syncthreads();
+      constexpr int par0 = 0;
       // GEMV, warp per live column (two columns at a time, four rows per lane in flight -> 8 independent 16-byte loads
       // per lane: the stage is latency-bound otherwise):  sdot[c] = sum_{i>=k} conj(a_c[i]) v_k[i]
       for (int lc = warp; lc < nown; lc += 2 * QR_NW) {
@@ -260,16 +306,26 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
         const cplx* W1 = W + (long)(c_lo + (live1 ? lc2 : lc)) * n;
         double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
         int i = k + lane;
+        for (; i + 224 < n; i += 256) {      // 16 independent 16-byte loads per lane in flight
+          cplx a[8], c[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { a[u] = W0[i + 32 * u]; c[u] = W1[i + 32 * u]; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const cplx v = vbuf[i + 32 * u];
+            ar += a[u].x * v.x + a[u].y * v.y;  ai += a[u].x * v.y - a[u].y * v.x;
+            br += c[u].x * v.x + c[u].y * v.y;  bi += c[u].x * v.y - c[u].y * v.x;
+          }
+        }
         for (; i + 96 < n; i += 128) {
-          cplx a[4], c[4], v[4];
+          cplx a[4], c[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) { a[u] = W0[i + 32 * u]; c[u] = W1[i + 32 * u]; }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = vbuf[i + 32 * u];
-#pragma unroll
           for (int u = 0; u < 4; ++u) {
-            ar += a[u].x * v[u].x + a[u].y * v[u].y;  ai += a[u].x * v[u].y - a[u].y * v[u].x;
-            br += c[u].x * v[u].x + c[u].y * v[u].y;  bi += c[u].x * v[u].y - c[u].y * v[u].x;
+            const cplx v = vbuf[i + 32 * u];
+            ar += a[u].x * v.x + a[u].y * v.y;  ai += a[u].x * v.y - a[u].y * v.x;
+            br += c[u].x * v.x + c[u].y * v.y;  bi += c[u].x * v.y - c[u].y * v.x;
           }
         }
         for (; i < n; i += 32) {
@@ -295,8 +351,8 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
           cplx rk = Wc[k];
           for (int tt = 0; tt < t; ++tt) {
             const cplx ft = Ft[(long)tt * ncc + lc];
-            cfma(f, ft, bc[par].aux[tt]);
-            const cplx vr = bc[par].vrow[tt];
+            cfma(f, ft, bc[par0].aux[tt]);
+            const cplx vr = bc[par0].vrow[tt];
             rk.x -= vr.x * ft.x + vr.y * ft.y;     // vrow * conj(F)
             rk.y -= vr.y * ft.x - vr.x * ft.y;
           }
@@ -313,6 +369,38 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
             else vn1[lc] = v1 * sqrt(temp);
           }
         }
+      }
+      __syncthreads();
+      // Flagged columns get their partial norm recomputed exactly (dznrm2 of the rows below the pivot row).  zlaqps
+      // closes the panel for that, because the column must be up to date first; on graded matrices (the metric spans
+      // 15 decades) some column asks for it at almost every step, which would degrade the panel to width 1 and triple
+      // the memory traffic.  Here the pending reflectors of the panel are applied to the flagged column on the fly
+      // (same values, the panel stays open): u = a_c - sum_{tt<=t} v_tt conj(F[c][tt]), rows > k.
+      for (int lc = warp; lc < nown; lc += QR_NW) {
+        if (!mark[lc]) continue;                      // warp-uniform
+        const cplx* Wc = W + (long)(c_lo + lc) * n;
+        double ssq = 0.0;
+        for (int i = k + 1 + lane; i < n; i += 32) {
+          cplx u = Wc[i];
+          for (int t0 = 0; t0 <= t; t0 += 8) {
+            cplx vv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              vv[q] = (t0 + q <= t) ? __ldcg(V + (long)(j0 + t0 + q) * n + i) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (t0 + q <= t) {
+                const cplx f = Ft[(long)(t0 + q) * ncc + lc];
+                u.x -= vv[q].x * f.x + vv[q].y * f.y;
+                u.y -= vv[q].y * f.x - vv[q].x * f.y;
+              }
+            }
+          }
+          ssq += u.x * u.x + u.y * u.y;
+        }
+        ssq = warp_sum(ssq);
+        __syncwarp();
+        if (lane == 0) { const double nr = sqrt(ssq); vn1[lc] = nr; vn2[lc] = nr; mark[lc] = 0; }
       }
       __syncthreads();
       ++t; ++k;
@@ -580,7 +668,7 @@ __global__ void gelsy_extract_kernel(const cplx* __restrict__ Gall, const cplx* 
     const double den = tau.x * tau.x + tau.y * tau.y;
     s = (k < r && den != 0.0) ? make_double2(tau.x / den, -tau.y / den) : make_double2(1.0, 0.0);
   } else if (k < j && j < r) {
-    s = G[(long)k * rP + j];
+    s = G[(long)j * rP + k];       // g = Vt Vt^H = (V^H V)^T: the strict upper triangle of V^H V sits in g's lower one
   }
   if (k <= j && j < r) { const cplx a = Vall[(long)b * strideV + (long)k * n + j]; v = make_double2(a.x, -a.y); }
   Sall[(long)b * rP * rP + (long)k * rP + j] = s;
@@ -637,6 +725,22 @@ __global__ void gelsy_q1_finish_kernel(cplx* __restrict__ VM, const double* __re
   *q = make_double2(((i == j ? 1.0 : 0.0) - v.x) * d, -v.y * d);
 }
 
+// Transposed form: on entry t1[j][i] = sum_k M[k][j] V[k][i] (= conj of (V M)^H); on return
+// q1h[j][i] = conj(q1s[i][j]) = (delta_ij - conj(t1[j][i])) * dinv[j]  (rows j >= rank zero): D^-1 Q1^H, [rP x n].
+__global__ void gelsy_q1h_finish_kernel(cplx* __restrict__ T1, const double* __restrict__ dinvall,
+                                        const int* __restrict__ rank, int n, int rP) {
+  const int b = blockIdx.z;
+  const int r = rank[b];
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= rP || i >= n) return;
+  cplx* q = T1 + (long)b * rP * n + (long)j * n + i;
+  if (j >= r) { *q = make_double2(0.0, 0.0); return; }
+  const double d = dinvall[(long)b * rP + j];
+  const cplx v = *q;
+  *q = make_double2(((i == j ? 1.0 : 0.0) - v.x) * d, v.y * d);
+}
+
 // w = (w + w^H) / 2 with an exactly real diagonal
 __global__ void hermitize_kernel(cplx* __restrict__ Wm, int n) {
   const int b = blockIdx.z;
@@ -676,7 +780,7 @@ extern "C" int isdf_qrcp(void* hv, void* a, int n, int batch, void* vt, void* ta
   size_t smem = 0;
   for (;; cs /= 2) {
     ncc = (n + cs - 1) / cs;
-    const long budget = (long)h->max_smem_optin - 4096;
+    const long budget = (long)h->max_smem_optin - 24 * 1024;    // static shared memory of the kernel
     bool ok = ncc <= QR_THREADS * QR_NCOLT;
     if (ok) {
       nb = QR_NB_MAX;
@@ -729,7 +833,7 @@ extern "C" int isdf_gelsy_rank(void* hv, const void* a, const int* piv, int n, i
   return ISDF_OK;
 }
 
-/* g [batch][rP][rP] = V^H V restricted to the first rP reflectors.  Outputs s, v1h [batch][rP][rP], dinv [batch][rP]. */
+/* g [batch][rP][rP] = Vt Vt^H = (V^H V)^T restricted to the first rP reflectors (lower triangle read).  Outputs s, v1h [batch][rP][rP], dinv [batch][rP]. */
 extern "C" int isdf_gelsy_extract(void* hv, const void* g, const void* tau, const int* rank, const void* vt,
                                   const void* a, const int* piv, int n, int rP, int batch, void* s, void* v1h,
                                   double* dinv, void* stream) {
@@ -762,6 +866,16 @@ extern "C" int isdf_gelsy_q1_finish(void* hv, void* vm, const double* dinv, cons
   ISDF_CHECK_ARG(h, vm && dinv && rank && n >= 1 && rP >= 1 && batch >= 1 && batch <= 65535, "args");
   dim3 block(32, 8), grid((rP + 31) / 32, (n + 7) / 8, batch);
   gelsy_q1_finish_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((cplx*)vm, dinv, rank, n, rP);
+  ISDF_LAUNCH_CHECK(h);
+  return ISDF_OK;
+}
+
+extern "C" int isdf_gelsy_q1h_finish(void* hv, void* t1, const double* dinv, const int* rank, int n, int rP, int batch,
+                                     void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, t1 && dinv && rank && n >= 1 && rP >= 1 && batch >= 1 && batch <= 65535, "args");
+  dim3 block(32, 8), grid((n + 31) / 32, (rP + 7) / 8, batch);
+  gelsy_q1h_finish_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((cplx*)t1, dinv, rank, n, rP);
   ISDF_LAUNCH_CHECK(h);
   return ISDF_OK;
 }

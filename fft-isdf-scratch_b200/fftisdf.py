@@ -237,18 +237,16 @@ def build(df_obj):
         if mine:
             with ops.timed("gelsy_operators"):
                 fac = ops.gelsy_operators(qr_state, nipP)
-            q1_l, lf_l, eh_l = fac["q1s"], fac["lfwd"], fac["eh"]
+            gt_l, eh_l = fac["gt"], fac["eh"]
             del fac
         else:
-            q1_l = torch.zeros((0, nip, nipP), dtype=torch.complex128, device=dev)
-            lf_l = torch.zeros((0, nipP, nipP), dtype=torch.complex128, device=dev)
+            gt_l = torch.zeros((0, nipP, nip), dtype=torch.complex128, device=dev)
             eh_l = torch.zeros((0, nipP, nip), dtype=torch.complex128, device=dev)
         del qr_state
-        q1s = sharding.AsyncSlotGather(q1_l, nq, comm).result()     # needed by the first grid block
-        lfwd_g = sharding.AsyncSlotGather(lf_l, nq, comm)
+        gt = sharding.AsyncSlotGather(gt_l, nq, comm).result()      # needed by the first grid block
         ehg = sharding.AsyncSlotGather(eh_l, nq, comm)
-        ubwd_g = None
-        del q1_l, lf_l, eh_l
+        lfwd_g = ubwd_g = None
+        del gt_l, eh_l
         rowmap = None
     else:
         piv_h = piv_q.cpu().numpy()
@@ -318,8 +316,8 @@ def build(df_obj):
                         ops.ktransform_rows(fxt, nip * sb, sb, yv, nip * sb, sb, 0, nip, sb, kmesh, uax_h,
                                             conj2=0, qslot=qslot, diag=diag[2:4])                           # :79-85
                     c0 = g0 - g_lo + s0
-                    with ops.timed("q1_gemm"):
-                        ops.gemm_hn_strided(q1s, yv, theta[:, :, c0:c0 + sb])  # (Q1 D^-1)^H Y^T  (zunmqr of zgelsy, :108)
+                    with ops.timed("fit_gemm"):
+                        ops.gemm_nn_strided(gt, yv, theta[:, :, c0:c0 + sb])   # Theta~ = (U^-H D^-1 Q1^H) Y^T   (:108)
                 else:
                     with ops.timed("ktransform"):
                         ops.ktransform_rows(fxt, nip * sb, sb, theta, nipP * ncol, ncol, g0 - g_lo + s0, nip, sb, kmesh,
@@ -336,7 +334,8 @@ def build(df_obj):
                 ops.ktransform_square(fx, blk * nip, nip, yv, nip * blk, 1, blk, 0, blk, nip, kmesh, uax,
                                       conj2=0, out_g_fast=1, qslot=qslot, diag=diag[2:4])                  # :79-85
                 c0 = g0 - g_lo
-                ops.gemm_hn_strided(q1s, yv, theta[:, :, c0:c0 + blk])
+                with ops.timed("fit_gemm"):
+                    ops.gemm_nn_strided(gt, yv, theta[:, :, c0:c0 + blk])
             else:
                 ops.ktransform_square(fx, blk * nip, nip, theta, nipP * ncol, 1, ncol, g0 - g_lo, blk, nip, kmesh, uax,
                                       conj2=0, out_g_fast=1, qslot=qslot, rowmap=rowmap, rowmap_sq=nip,
@@ -350,13 +349,9 @@ def build(df_obj):
     # ---- C(b). Theta_q = A_q^+ Y_q^T, all q at once                                        :108
     rmax = int(rank_h.max())
     if fit == "gelsy":
-        # ztrsm of zgelsy: Theta~ = T11^-1 (Q1^H Y^T), here with T11 = D U^H (lower triangular) -> forward substitution;
-        # Theta = E Theta~ is never formed: W_q = E (Theta~ K Theta~^H) E^H with orthonormal E
-        lfwd = lfwd_g.result()
-        del lfwd_g, q1s
-        with ops.timed("sweep"):
-            ops.trsm_sweep(lfwd, theta, nact=rmax, backward=False, ng=ncol)
-        del lfwd
+        # zunmqr + ztrsm of zgelsy were applied block by block above (Theta~ = G Y^T); Theta = E Theta~ is never formed:
+        # W_q = E (Theta~ K Theta~^H) E^H with orthonormal E
+        del gt
     else:
         lfwd, ubwd = lfwd_g.result(), ubwd_g.result()
         del lfwd_g, ubwd_g

@@ -347,37 +347,52 @@ class IsdfOps:
             rank = self.gelsy_rank(w, piv, rcond)
         return dict(w=w, vt=vt, tau=tau, piv=piv, pos=pos, rank=rank)
 
-    def gelsy_operators(self, st, rP):
-        """Stage 2: the three dense operators of x = P Z^H [T11^-1 (Q^H b)(:rank); 0] for every matrix of the batch:
-             q1s  [batch, n, rP]   Q1 D^-1 (orthonormal columns scaled by 1/|R_kk|, zero beyond rank)
-             lfwd [batch, rP, rP]  block operator of the forward substitution with U^H, D^-1 [R11 R12] P^T = U^H E^H
-             eh   [batch, rP, n]   E^H (orthonormal rows, zero beyond rank)
-           so that  Theta~ = U^-H (q1s^H Y^T)  [rank x ng]  and  Theta = eh^H Theta~,  W = eh^H W~ eh."""
+    def gelsy_operators(self, st, rP, debug=False):
+        """Stage 2: the dense operators of x = P Z^H [T11^-1 (Q^H b)(:rank); 0] for every matrix of the batch:
+             gt   [batch, rP, n]   G = U^-H D^-1 Q1^H  (zunmqr + ztrsm of zgelsy as ONE operator: U^-H is lower triangular
+                                   and well conditioned, so row i of G carries the single scale 1/|R_ii| and the
+                                   explicit product is row-wise as accurate as the two-step application)
+             eh   [batch, rP, n]   E^H (orthonormal rows, zero beyond rank; E = P Z1^H of ztzrzf/zunmrz)
+           so that  Theta~ = G Y^T  [rank x ng],  Theta = eh^H Theta~  and  W = eh^H W~ eh.
+           D = |diag R|;  D^-1 [R11 R12] P^T = U^H E^H by Cholesky-QR (twice) with U upper triangular.
+           debug=True also returns q1s [batch, n, rP] = Q1 D^-1 and lfwd (the block operator of U^-H)."""
         w, vt, tau, piv, pos, rank = st["w"], st["vt"], st["tau"], st["piv"], st["pos"], st["rank"]
         batch, n, _ = w.shape
         assert rP % TB == 0
         kk = min(rP, n)
         ident = torch.arange(rP, dtype=torch.int32, device=self.device).repeat(batch, 1).contiguous()
-        # --- Q1 through the compact-WY form of the first `rank` reflectors
+        # --- Q1 through the compact-WY form of the first `rank` reflectors: Q1 = I(:, :r) - V S^-1 V(:r, :)^H
         vv = vt[:, :kk, :]
-        g = torch.zeros((batch, rP, rP), dtype=c128, device=self.device)
-        self.gram_conja_strided(vv, vv, g[:, :kk, :kk])                      # V^H V
+        with self.timed("ops_vhv"):
+            # V^H V as conj(Vt Vt^H): HERK (half the flops); only the strict upper triangle of V^H V is used,
+            # i.e. the lower triangle of Vt Vt^H transposed -- the extract kernel reads g[j][k] for k < j
+            g = torch.zeros((batch, rP, rP), dtype=c128, device=self.device)
+            self.herk_strided(vv, n, n * n, kk, n, 1.0, None, 0, g, rP, rP * rP, batch)
         s = torch.empty((batch, rP, rP), dtype=c128, device=self.device)
         m = torch.empty((batch, rP, rP), dtype=c128, device=self.device)
         dinv = torch.empty((batch, rP), dtype=torch.float64, device=self.device)
-        self.handle.check(self.lib.isdf_gelsy_extract(self.h, _ptr(g), _ptr(tau), _ptr(rank), _ptr(vt), _ptr(w),
-                                                      _ptr(piv), n, rP, batch, _ptr(s), _ptr(m), _ptr(dinv),
-                                                      _stream()), "isdf_gelsy_extract")
-        self.launches += 1
-        _, ub = self.trsm_prepare(s, ident, rank, rP)
-        self.trsm_sweep(ub, m, backward=True)                                 # M = S^-1 V1^H
+        with self.timed("ops_wy_solve"):
+            self.handle.check(self.lib.isdf_gelsy_extract(self.h, _ptr(g), _ptr(tau), _ptr(rank), _ptr(vt), _ptr(w),
+                                                          _ptr(piv), n, rP, batch, _ptr(s), _ptr(m), _ptr(dinv),
+                                                          _stream()), "isdf_gelsy_extract")
+            self.launches += 1
+            _, ub = self.trsm_prepare(s, ident, rank, rP)
+            self.trsm_sweep(ub, m, backward=True)                             # M = S^-1 V1^H
         del s, ub, g
-        q1s = torch.zeros((batch, n, rP), dtype=c128, device=self.device)
-        self.gemm_tn_into(vv, m[:, :kk, :], q1s)                              # V M
+        with self.timed("ops_q1h"):
+            gt = torch.zeros((batch, rP, n), dtype=c128, device=self.device)
+            self.gemm_tn_into(m[:, :kk, :], vv, gt)                           # M^T V  = conj((V M)^H)
+            self.handle.check(self.lib.isdf_gelsy_q1h_finish(self.h, _ptr(gt), _ptr(dinv), _ptr(rank), n, rP, batch,
+                                                             _stream()), "isdf_gelsy_q1h_finish")   # D^-1 Q1^H
+            self.launches += 1
+        out = {}
+        if debug:
+            q1s = torch.zeros((batch, n, rP), dtype=c128, device=self.device)
+            self.gemm_tn_into(vv, m[:, :kk, :], q1s)
+            self.handle.check(self.lib.isdf_gelsy_q1_finish(self.h, _ptr(q1s), _ptr(dinv), _ptr(rank), n, rP, batch,
+                                                            _stream()), "isdf_gelsy_q1_finish")
+            out["q1s"] = q1s
         del m
-        self.handle.check(self.lib.isdf_gelsy_q1_finish(self.h, _ptr(q1s), _ptr(dinv), _ptr(rank), n, rP, batch,
-                                                        _stream()), "isdf_gelsy_q1_finish")
-        self.launches += 1
         # --- E^H and the triangular factor: Cholesky-QR (twice) of the row-scaled [R11 R12] P^T
         eh = torch.empty((batch, rP, n), dtype=c128, device=self.device)
         self.handle.check(self.lib.isdf_gelsy_rhat(self.h, _ptr(w), _ptr(pos), _ptr(dinv), _ptr(rank), n, rP, batch,
@@ -385,15 +400,35 @@ class IsdfOps:
         self.launches += 1
         us = []
         for _ in range(2):
-            gg = self.herk(eh)
-            u, _, rk = self.chol_nopivot(gg)
-            lf, _ = self.trsm_prepare(u, ident, rk, rP)
-            self.trsm_sweep(lf, eh, backward=False)
+            with self.timed("ops_cholqr_herk"):
+                gg = self.herk(eh)
+            with self.timed("ops_cholqr_chol"):
+                u, _, rk = self.chol_nopivot(gg)
+            with self.timed("ops_cholqr_solve"):
+                lf, _ = self.trsm_prepare(u, ident, rk, rP)
+                self.trsm_sweep(lf, eh, backward=False)
             us.append(u)
             del gg, lf
-        ucomb = self.gemm_nn(us[1], us[0])                                    # U = U2 U1
-        lfwd, _ = self.trsm_prepare(ucomb, ident, rank, rP)
-        return dict(q1s=q1s, lfwd=lfwd, eh=eh, chol_rank=rk)
+        with self.timed("ops_g"):
+            ucomb = self.gemm_nn(us[1], us[0])                                # U = U2 U1
+            del us
+            lfwd, _ = self.trsm_prepare(ucomb, ident, rank, rP)
+            self.trsm_sweep(lfwd, gt, backward=False)                         # G = U^-H (D^-1 Q1^H)
+        out.update(gt=gt, eh=eh, chol_rank=rk)
+        if debug:
+            out["lfwd"] = lfwd
+        return out
+
+    def gemm_nn_strided(self, a, b, out):
+        """out[z] = a[z] @ b[z] into a strided view: a [batch,m,k], b [batch,k,n], out [batch,m,n] (unit last stride)."""
+        assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
+        batch, m, k = a.shape
+        n = b.shape[2]
+        self.handle.check(self.lib.isdf_gemm_nn(self.h, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1),
+                                                b.stride(0), _ptr(out), out.stride(1), out.stride(0), m, n, k, batch,
+                                                _stream()), "isdf_gemm_nn")
+        self.launches += 1
+        return out
 
     def gram_conja_strided(self, a, b, out):
         assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1

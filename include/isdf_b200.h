@@ -157,7 +157,7 @@ int isdf_gelsy_rank(void* handle, const void* a, const int* piv, int n, int batc
  * (zunmqr, ztrsm, ztzrzf/zunmrz) is applied to all right-hand sides (sequenced by kernels.py:gelsy_factor):
  *   Q1 D^-1  = (I(:, :rank) - V S^-1 V(:rank, :)^H) D^-1,  S = diag(1/tau) + striu(V^H V)   (compact WY, D = |diag R|)
  *   E^H      = rows of D^-1 [R11 R12] P^T orthonormalised by Cholesky-QR (twice), U = their triangular factor
- * isdf_gelsy_extract: g [batch][rP][rP] = V^H V  ->  s, v1h [batch][rP][rP] (S and V(:rank,:)^H), dinv [batch][rP].
+ * isdf_gelsy_extract: g [batch][rP][rP] = vt vt^H = (V^H V)^T (lower triangle read)  ->  s, v1h [batch][rP][rP] (S and V(:rank,:)^H), dinv [batch][rP].
  * isdf_gelsy_rhat: rhat [batch][rP][n] = D^-1 [R11 R12] P^T (original column order, zero rows beyond rank).
  * isdf_gelsy_q1_finish: vm [batch][n][rP] = V S^-1 V1^H on entry, Q1 D^-1 on return (zero columns beyond rank).
  * isdf_hermitize: w <- (w + w^H)/2.  isdf_gemm_tn: c = a^T b (no conjugation), a [k][m], b [k][n]. */
@@ -167,6 +167,9 @@ int isdf_gelsy_rhat(void* handle, const void* a, const int* pos, const double* d
                     int batch, void* rhat, void* stream);
 int isdf_gelsy_q1_finish(void* handle, void* vm, const double* dinv, const int* rank, int n, int rP, int batch,
                          void* stream);
+/* Transposed twin: t1 [batch][rP][n] = M^T V on entry, D^-1 Q1^H on return (zero rows beyond rank). */
+int isdf_gelsy_q1h_finish(void* handle, void* t1, const double* dinv, const int* rank, int n, int rP, int batch,
+                          void* stream);
 int isdf_hermitize(void* handle, void* w, int n, int batch, void* stream);
 int isdf_gemm_tn(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB, void* c,
                  long ldc, long strideC, int m, int n, int k, int batch, void* stream);

@@ -102,7 +102,7 @@ def test_gelsy_operators_and_solution(n, r, decay, seed):
     st = ops.gelsy_qr(_dev(np.stack([a, a])), EPS)
     rank = st["rank"].cpu().numpy()
     rP = max(64, -(-int(rank.max()) // 64) * 64)
-    fac = ops.gelsy_operators(st, rP)
+    fac = ops.gelsy_operators(st, rP, debug=True)
     assert np.array_equal(fac["chol_rank"].cpu().numpy(), rank)
     rk = int(rank[0])
     q1s, eh = fac["q1s"].cpu().numpy()[0], fac["eh"].cpu().numpy()[0]
@@ -114,13 +114,19 @@ def test_gelsy_operators_and_solution(n, r, decay, seed):
     assert np.abs(q1s[:, rk:]).max() == 0.0 if rk < rP else True
     assert np.abs(q1.conj().T @ a[:, piv] - rr[:rk]).max() < 1e-12 * np.abs(a).max() * n ** 0.5
     assert np.abs(eh[:rk] @ eh[:rk].conj().T - np.eye(rk)).max() < 1e-12
-    # device solve
+    # device solve, two-step form:  x = E U^-H ((Q1 D^-1)^H b)
     bt = _dev(np.stack([b, b]))
     c = ops.gemm_hn(fac["q1s"], bt)                                        # [2, rP, 9]
     cpad = torch.zeros((2, rP, 64), dtype=torch.complex128, device=c.device)
     cpad[:, :, :9] = c
     ops.trsm_sweep(fac["lfwd"], cpad, nact=int(rank.max()), backward=False, ng=9)
-    x = ops.gemm_hn(fac["eh"], cpad.contiguous())[:, :, :9].cpu().numpy()
+    x2 = ops.gemm_hn(fac["eh"], cpad.contiguous())[:, :, :9].cpu().numpy()
+    # ... and the fused operator the build uses:  x = E (G b),  G = U^-H D^-1 Q1^H
+    x = ops.gemm_hn(fac["eh"], ops.gemm_nn(fac["gt"], bt)).cpu().numpy()
+    d_all = np.abs(np.diag(rr))[:rk]
+    assert np.abs(x - x2).max() < max(1e-11, 50 * d_all[0] / d_all[-1] * EPS) * np.abs(x2).max(), np.abs(x - x2).max() / np.abs(x2).max()
+    gt = fac["gt"].cpu().numpy()[0]
+    assert np.abs(gt[rk:]).max() == 0.0 if rk < rP else True
     ref = scipy.linalg.lstsq(a, b, lapack_driver="gelsy")
     xp, rkp = GP.gelsy(a, b)
     # residual and (when the ranks agree) the solution itself

@@ -244,9 +244,11 @@ def build(df_obj):
             eh_l = torch.zeros((0, nipP, nip), dtype=torch.complex128, device=dev)
         del qr_state
         gt = sharding.AsyncSlotGather(gt_l, nq, comm).result()      # needed by the first grid block
-        ehg = sharding.AsyncSlotGather(eh_l, nq, comm)
+        # E stays with the rank that factorised the slot: W~ is all-reduced and every rank expands its own slots;
+        # only `keep_theta` needs E everywhere
+        ehg = sharding.AsyncSlotGather(eh_l, nq, comm) if getattr(df_obj, "keep_theta", False) else None
         lfwd_g = ubwd_g = None
-        del gt_l, eh_l
+        del gt_l
         rowmap = None
     else:
         piv_h = piv_q.cpu().numpy()
@@ -273,6 +275,20 @@ def build(df_obj):
     # Y^T, then Theta, then B (in place).  Multi-GPU with a tensor-core-DFT mesh: the buffer lives in NVLink
     # peer-mapped memory so that the FFT kernels gather/scatter it directly (no all-to-all, no permute copies).
     p2p = world > 1 and all(2 <= m <= 48 for m in mesh) and getattr(df_obj, "exchange", "p2p") == "p2p"
+    # Memory guard (the reference raises RuntimeError on a shortfall, fftdf-with-k.py:41-48): the one O(nq nip ng)
+    # object is Theta; the per-block scratch (fx^T for all k, Y^T for all q) is sized to what is left.
+    blksize = int(df_obj.blksize)
+    need_theta = 16.0 * nq * nipP * ncol
+    cached = p2p and (nq, nipP, ncol) in df_obj.__dict__.get("_peer_cache", {})
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    free_b += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)      # torch's cached, reusable blocks
+    per_col = 16.0 * nip * (nkpt + (nq if fit == "gelsy" else 0))                       # scratch bytes per grid column
+    left = free_b - (0.0 if cached else need_theta) - 16.0 * ngrid * 6 - (2 << 30)
+    if left < per_col * 64:
+        raise RuntimeError("ISDF build needs %.1f GB for Theta (nq=%d x nipP=%d x %d grid columns) plus scratch, only "
+                           "%.1f GB of device memory are free: use more GPUs (grid columns are sharded) or a smaller c0"
+                           % (need_theta / 1e9, nq, nipP, ncol, free_b / 1e9))
+    sub_cap = max(64, int(min(left * 0.5, 48e9) // per_col) // 64 * 64)                # columns per RHS sub-block
     if p2p:
         cache = df_obj.__dict__.setdefault("_peer_cache", {})   # symmetric allocations are reused across builds
         key = (nq, nipP, ncol)
@@ -284,7 +300,6 @@ def build(df_obj):
         theta.zero_()
     else:
         theta = torch.zeros((nq, nipP, ncol), dtype=torch.complex128, device=dev)
-    blksize = int(df_obj.blksize)
     fx_k = None
     y_blk = None        # gelsy: Y^T of one grid block [nq, nip, blk] (natural row order), projected by Q1^H at once
     if upload_done is not None:
@@ -300,7 +315,7 @@ def build(df_obj):
         if reg_path:
             # transposed product fx^T[k][I][g] = X_k F_k^H (:76), so the elementwise stage streams along g
             # (optionally in L2-sized sub-blocks, see rhs_l2_bytes)
-            sub = max(64, min(blk, int(df_obj.rhs_l2_bytes // (nkpt * nip * 16)) // 64 * 64))
+            sub = max(64, min(blk, sub_cap, int(df_obj.rhs_l2_bytes // (nkpt * nip * 16)) // 64 * 64))
             if fx_k is None or fx_k.numel() != nkpt * sub * nip:
                 fx_k = torch.empty((nkpt * sub * nip,), dtype=torch.complex128, device=dev)
             if fit == "gelsy" and (y_blk is None or y_blk.numel() != nq * nip * sub):
@@ -410,11 +425,15 @@ def build(df_obj):
         with ops.timed("herk"):
             ops.herk_strided(theta, ncol, nipP * ncol, rmax, ncol, 1.0, None, 0, wt, nipP, nipP * nipP, nq)  # :121
         sharding.allreduce_sum_(wt, comm)
-        eh = ehg.result()
-        del ehg
-        with ops.timed("expand_w"):
-            wslot = ops.hermitize(ops.gemm_hn(eh, ops.gemm_nn(wt, eh)))    # W_q = E W~ E^H
-        del wt, eh
+        with ops.timed("expand_w"):                                        # W_q = E W~ E^H for this rank's slots
+            if mine:
+                wt_l = wt[mine].contiguous() if world > 1 else wt
+                w_l = ops.hermitize(ops.gemm_hn(eh_l, ops.gemm_nn(wt_l, eh_l)))
+                del wt_l
+            else:
+                w_l = torch.zeros((0, nip, nip), dtype=torch.complex128, device=dev)
+        wslot = sharding.allgather_slots(w_l, nq, comm)
+        del wt, eh_l, w_l
     else:
         wslot = torch.zeros((nq, nip, nip), dtype=torch.complex128, device=dev)
         nrow = min(nip, rmax)

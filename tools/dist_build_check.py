@@ -18,7 +18,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     worst = 0.0
-    for name in ["k231_odd", "k321_spd", "gamma_s", "k222_sp"]:
+    for name in ["k231_odd", "k321_spd", "gamma_s", "k222_sp", "k221_rd"]:
         g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", f"ref_{name}.npz"))
         cell = pk.TableCell(g["a"], g["mesh"], g["x0"].shape[-1])
 

@@ -25,6 +25,7 @@
 // A panel ends after nb steps; the owner CTAs then apply the deferred rank-nb update to their columns.  (zlaqps also
 // ends it when a column asks for its norm to be recomputed; here that column is brought up to date on the fly.)
 #include <float.h>
+#include <stdlib.h>
 #include <cooperative_groups.h>
 #include "gemm_c128.cuh"
 
@@ -376,11 +377,13 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
       // 15 decades) some column asks for it at almost every step, which would degrade the panel to width 1 and triple
       // the memory traffic.  Here the pending reflectors of the panel are applied to the flagged column on the fly
       // (same values, the panel stays open): u = a_c - sum_{tt<=t} v_tt conj(F[c][tt]), rows > k.
-      for (int lc = warp; lc < nown; lc += QR_NW) {
-        if (!mark[lc]) continue;                      // warp-uniform
+      // (the whole CTA works on one flagged column at a time: a single warp would need ~50 us per column, and every
+      //  other CTA of the cluster waits for it at the next barrier)
+      for (int lc = 0; lc < nown; ++lc) {
+        if (!mark[lc]) continue;                      // block-uniform (shared memory, synchronised above)
         const cplx* Wc = W + (long)(c_lo + lc) * n;
         double ssq = 0.0;
-        for (int i = k + 1 + lane; i < n; i += 32) {
+        for (int i = k + 1 + tid; i < n; i += QR_THREADS) {
           cplx u = Wc[i];
           for (int t0 = 0; t0 <= t; t0 += 8) {
             cplx vv[8];
@@ -399,8 +402,15 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
           ssq += u.x * u.x + u.y * u.y;
         }
         ssq = warp_sum(ssq);
-        __syncwarp();
-        if (lane == 0) { const double nr = sqrt(ssq); vn1[lc] = nr; vn2[lc] = nr; mark[lc] = 0; }
+        if (lane == 0) red_v[warp] = ssq;
+        __syncthreads();
+        if (tid == 0) {
+          double tot = 0.0;
+          for (int w = 0; w < QR_NW; ++w) tot += red_v[w];
+          const double nr = sqrt(tot);
+          vn1[lc] = nr; vn2[lc] = nr; mark[lc] = 0;
+        }
+        __syncthreads();
       }
       __syncthreads();
       ++t; ++k;
@@ -773,8 +783,12 @@ extern "C" int isdf_qrcp(void* hv, void* a, int n, int batch, void* vt, void* ta
   cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, a && vt && tau && piv && pos, "null pointer");
   ISDF_CHECK_ARG(h, n >= 1 && batch >= 1 && batch <= 65535, "shape");
-  int cs = (n >= 1024) ? 16 : 8;
+  // Large matrices: 16-CTA clusters when the batch leaves SMs idle otherwise (one 16-cluster per GPC: 8 at a time),
+  // 8-CTA clusters (16 at a time) when there are more matrices than that -- measured on B200 at n = 3120:
+  // 5 matrices 336 ms vs 498 ms, 36 matrices 2031 ms vs 1687 ms.
+  int cs = (n >= 1024 && batch <= 8) ? 16 : 8;
   if (n < 64) cs = 1; else if (n < 256) cs = 2;
+  if (const char* e = getenv("ISDF_QR_CS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) cs = v; }   // tuning
   ISDF_CUDA(h, cudaFuncSetAttribute(qrcp_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   int ncc = 0, nb = 0, nvb = 0;
   size_t smem = 0;

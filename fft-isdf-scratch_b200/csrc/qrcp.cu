@@ -37,6 +37,7 @@ constexpr int QR_THREADS = 512;
 constexpr int QR_NW = QR_THREADS / 32;
 constexpr int QR_NB_MAX = 32;
 constexpr int QR_CS_MAX = 16;
+constexpr int QR_NSL = 16;             // logical row slices of the pivot column (independent of the cluster size)
 constexpr int QR_NCOLT = 2;            // columns per thread in the per-column phases -> ncc <= 1024
 constexpr int QR_RT_MIN = 64;          // rows per trailing-update tile (lower bound)
 
@@ -91,9 +92,11 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
   int* mark = pos + ncc;                                          // [ncc]
   __shared__ QrCand cand[2][QR_CS_MAX];
   __shared__ QrBcast bc[1];
-  __shared__ QrPart part[2][QR_CS_MAX];
+  __shared__ QrPart part[2][QR_NSL];
   __shared__ cplx fp[QR_NB_MAX];
-  __shared__ cplx mydots[QR_NB_MAX];
+  __shared__ cplx mydots[QR_NSL * QR_NB_MAX];
+  __shared__ cplx tdots[QR_NB_MAX];
+  __shared__ double s_nrm[QR_NSL];
   __shared__ double red_v[QR_NW];
   __shared__ int red_pos[QR_NW], red_idx[QR_NW], red_flag[QR_NW];
   __shared__ double s_scal[6];     // beta, tau.re, tau.im, scale.re, scale.im, spare
@@ -188,74 +191,85 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
         fp[tid] = Fo[(long)tid * ncc + lp];
       }
       __syncthreads();
-      const int sl = (n - k + CS - 1) / CS;
-      const int i_lo = k + crank * sl;
-      const int cnt = max(0, min(sl, n - i_lo));
-      double ss = 0.0;
-      for (int r = tid; r < cnt; r += QR_THREADS) {
-        const int my_i = i_lo + r;
-        cplx a = __ldcg(W + (long)p * n + my_i);
-        // a_p -= sum_tt v_tt conj(F[p][tt]); loads in batches of 8 (the column of V is L2-resident, latency-bound)
-        for (int t0 = 0; t0 < t; t0 += 8) {
-          cplx vv[8];
+      // The rows [k, n) are cut into QR_NSL logical slices whatever the cluster size, every slice is reduced in a fixed
+      // order, and the slice partials are summed in slice order: the factorisation is bit-identical for every
+      // cluster size (the cluster size follows the number of matrices per GPU, i.e. the number of GPUs).
+      const int spc = QR_NSL / CS;                       // logical slices per CTA
+      const int sl = (n - k + QR_NSL - 1) / QR_NSL;      // rows per logical slice
+      for (int s_loc = 0; s_loc < spc; ++s_loc) {
+        const int i_lo = k + (crank * spc + s_loc) * sl;
+        const int cnt = max(0, min(sl, n - i_lo));
+        cplx* abuf = vbuf + (long)s_loc * sl;
+        double ss = 0.0;
+        for (int r = tid; r < cnt; r += QR_THREADS) {
+          const int my_i = i_lo + r;
+          cplx a = __ldcg(W + (long)p * n + my_i);
+          // a_p -= sum_tt v_tt conj(F[p][tt]); loads in batches of 8 (the column of V is L2-resident, latency-bound)
+          for (int t0 = 0; t0 < t; t0 += 8) {
+            cplx vv[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            vv[u] = (t0 + u < t) ? __ldcg(V + (long)(j0 + t0 + u) * n + my_i) : make_double2(0.0, 0.0);
+            for (int u = 0; u < 8; ++u)
+              vv[u] = (t0 + u < t) ? __ldcg(V + (long)(j0 + t0 + u) * n + my_i) : make_double2(0.0, 0.0);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (t0 + u < t) {
-              const cplx f = fp[t0 + u];
-              a.x -= vv[u].x * f.x + vv[u].y * f.y;      // vv * conj(f)
-              a.y -= vv[u].y * f.x - vv[u].x * f.y;
+            for (int u = 0; u < 8; ++u) {
+              if (t0 + u < t) {
+                const cplx f = fp[t0 + u];
+                a.x -= vv[u].x * f.x + vv[u].y * f.y;      // vv * conj(f)
+                a.y -= vv[u].y * f.x - vv[u].x * f.y;
+              }
             }
           }
+          abuf[r] = a;                                    // slice buffer (the previous reflector is dead by now)
+          if (my_i > k) ss += a.x * a.x + a.y * a.y;
         }
-        vbuf[r] = a;                                      // slice buffer (the previous reflector is dead by now)
-        if (my_i > k) ss += a.x * a.x + a.y * a.y;
-      }
-      ss = warp_sum(ss);
-      if (lane == 0) red_v[warp] = ss;
-      __syncthreads();
-      // partial dots[tt] = sum_{i in slice, i > k} conj(v_tt[i]) a[i]   (warp per tt)
-      for (int tt = warp; tt < t; tt += QR_NW) {
-        const cplx* Vt = V + (long)(j0 + tt) * n + i_lo;
-        double sr = 0.0, si = 0.0;
-        for (int r = lane; r < cnt; r += 32) {
-          if (i_lo + r > k) {
-            const cplx vv = __ldcg(Vt + r), av = vbuf[r];
-            sr += vv.x * av.x + vv.y * av.y;        // conj(vv) * av
-            si += vv.x * av.y - vv.y * av.x;
+        ss = warp_sum(ss);
+        if (lane == 0) red_v[warp] = ss;
+        __syncthreads();
+        if (tid == 0) {
+          double tot = 0.0;
+          for (int w = 0; w < QR_NW; ++w) tot += red_v[w];
+          s_nrm[s_loc] = tot;
+        }
+        // partial dots[tt] = sum_{i in slice, i > k} conj(v_tt[i]) a[i]   (warp per tt)
+        for (int tt = warp; tt < t; tt += QR_NW) {
+          const cplx* Vt = V + (long)(j0 + tt) * n + i_lo;
+          double sr = 0.0, si = 0.0;
+          for (int r = lane; r < cnt; r += 32) {
+            if (i_lo + r > k) {
+              const cplx vv = __ldcg(Vt + r), av = abuf[r];
+              sr += vv.x * av.x + vv.y * av.y;        // conj(vv) * av
+              si += vv.x * av.y - vv.y * av.x;
+            }
           }
+          sr = warp_sum(sr); si = warp_sum(si);
+          if (lane == 0) mydots[s_loc * QR_NB_MAX + tt] = make_double2(sr, si);
         }
-        sr = warp_sum(sr); si = warp_sum(si);
-        if (lane == 0) mydots[tt] = make_double2(sr, si);
+        __syncthreads();
       }
-      __syncthreads();
-      // publish {dots[0..t), a_k, |a|^2} into every CTA's table
+      // publish {dots[0..t), a_k, |a|^2} of every local slice into every CTA's table
       {
         const int nval = t + 2;
-        for (int e = tid; e < nval * CS; e += QR_THREADS) {
-          const int dst = e / nval, idx = e - dst * nval;
-          QrPart (*remote)[QR_CS_MAX] = cluster.map_shared_rank(part, dst);
-          if (idx < t) remote[par][crank].dots[idx] = mydots[idx];
-          else if (idx == t) remote[par][crank].ak = (crank == 0) ? vbuf[0] : make_double2(0.0, 0.0);
-          else {
-            double tot = 0.0;
-            for (int w = 0; w < QR_NW; ++w) tot += red_v[w];
-            remote[par][crank].nrm2 = tot;
-          }
+        for (int e = tid; e < nval * spc * CS; e += QR_THREADS) {
+          const int dst = e / (nval * spc);
+          const int rem = e - dst * (nval * spc);
+          const int s_loc = rem / nval, idx = rem - s_loc * nval;
+          const int sid = crank * spc + s_loc;
+          QrPart (*remote)[QR_NSL] = cluster.map_shared_rank(part, dst);
+          if (idx < t) remote[par][sid].dots[idx] = mydots[s_loc * QR_NB_MAX + idx];
+          else if (idx == t) remote[par][sid].ak = (sid == 0) ? vbuf[0] : make_double2(0.0, 0.0);
+          else remote[par][sid].nrm2 = s_nrm[s_loc];
         }
       }
       cluster.sync();
       // ---- every CTA: totals, zlarfg, auxv; scales and stores its slice of v_k
       if (tid < t) {
         double sr = 0.0, si = 0.0;
-        for (int r = 0; r < CS; ++r) { sr += part[par][r].dots[tid].x; si += part[par][r].dots[tid].y; }
-        mydots[tid] = make_double2(sr, si);
+        for (int r = 0; r < QR_NSL; ++r) { sr += part[par][r].dots[tid].x; si += part[par][r].dots[tid].y; }
+        tdots[tid] = make_double2(sr, si);
       }
       if (tid == 32) {
         double tot = 0.0;
-        for (int r = 0; r < CS; ++r) tot += part[par][r].nrm2;
+        for (int r = 0; r < QR_NSL; ++r) tot += part[par][r].nrm2;
         const cplx alpha = part[par][0].ak;
         double beta, tr, ti, sr, si;
         if (tot == 0.0 && alpha.y == 0.0) {
@@ -276,18 +290,23 @@ qrcp_cluster_kernel(cplx* __restrict__ Wall, long strideW, int n, int ncc, int n
       if (tid < t) {
         // auxv[tt] = -tau (conj(v_tt[k]) + scale * dots[tt]);  vrow[tt] = v_tt[k]
         const cplx vr = __ldcg(V + (long)(j0 + tid) * n + k);
-        const cplx sd = cmul(scal, mydots[tid]);
+        const cplx sd = cmul(scal, tdots[tid]);
         const cplx in = ident ? make_double2(0.0, 0.0) : make_double2(vr.x + sd.x, -vr.y + sd.y);
         bc[0].aux[tid] = make_double2(-(tau.x * in.x - tau.y * in.y), -(tau.x * in.y + tau.y * in.x));
         bc[0].vrow[tid] = vr;
       }
-      for (int r = tid; r < cnt; r += QR_THREADS) {
-        const int my_i = i_lo + r;
-        cplx v;
-        if (ident) v = make_double2(0.0, 0.0);
-        else if (my_i == k) v = make_double2(1.0, 0.0);
-        else v = cmul(vbuf[r], scal);
-        V[(long)k * n + my_i] = v;
+      for (int s_loc = 0; s_loc < spc; ++s_loc) {
+        const int i_lo = k + (crank * spc + s_loc) * sl;
+        const int cnt = max(0, min(sl, n - i_lo));
+        const cplx* abuf = vbuf + (long)s_loc * sl;
+        for (int r = tid; r < cnt; r += QR_THREADS) {
+          const int my_i = i_lo + r;
+          cplx v;
+          if (ident) v = make_double2(0.0, 0.0);
+          else if (my_i == k) v = make_double2(1.0, 0.0);
+          else v = cmul(abuf[r], scal);
+          V[(long)k * n + my_i] = v;
+        }
       }
       __syncthreads();    // the slice in vbuf is consumed before the full reflector overwrites it
       if (crank == owner && tid == 0) { W[(long)p * n + k] = make_double2(beta, 0.0); tau_out[k] = tau; }
@@ -769,7 +788,7 @@ __global__ void hermitize_kernel(cplx* __restrict__ Wm, int n) {
 using namespace isdf;
 
 static size_t qr_smem_bytes(int n, int ncc, int nb, int* nvb_out) {
-  const int nvb = n > nb * QR_RT_MIN ? n : nb * QR_RT_MIN;
+  const int nvb = (n > nb * QR_RT_MIN ? n : nb * QR_RT_MIN) + QR_NSL;   // + slack of the logical-slice layout
   if (nvb_out) *nvb_out = nvb;
   return (size_t)nvb * 16 + (size_t)nb * ncc * 16 + (size_t)ncc * (16 + 8 + 8 + 4 + 4);
 }
@@ -794,7 +813,7 @@ extern "C" int isdf_qrcp(void* hv, void* a, int n, int batch, void* vt, void* ta
   size_t smem = 0;
   for (;; cs /= 2) {
     ncc = (n + cs - 1) / cs;
-    const long budget = (long)h->max_smem_optin - 24 * 1024;    // static shared memory of the kernel
+    const long budget = (long)h->max_smem_optin - 34 * 1024;    // static shared memory of the kernel
     bool ok = ncc <= QR_THREADS * QR_NCOLT;
     if (ok) {
       nb = QR_NB_MAX;

@@ -136,3 +136,23 @@ def test_gelsy_operators_and_solution(n, r, decay, seed):
         nrm = np.abs(ref[0]).max()
         cond_r = d[0] / d[-1]
         assert np.abs(x[0] - ref[0]).max() < max(1e-10, 50 * cond_r * EPS) * nrm, (np.abs(x[0] - ref[0]).max() / nrm, cond_r)
+
+
+@pytest.mark.parametrize("n", [300, 1100])
+def test_qrcp_is_bit_identical_for_every_cluster_size(n):
+    """The cluster size follows the number of matrices per GPU (i.e. the number of GPUs); the factorisation must not
+    depend on it, so that an N-GPU build takes the very same rank decisions as the single-GPU build."""
+    import os
+    ops = _ops()
+    a = _psd(n, int(0.8 * n), 77, 9.0)
+    outs = []
+    for cs in ("4", "8", "16"):
+        os.environ["ISDF_QR_CS"] = cs
+        try:
+            st = ops.gelsy_qr(_dev(a[None]), EPS)
+        finally:
+            del os.environ["ISDF_QR_CS"]
+        outs.append([st[k].cpu().numpy() for k in ("w", "vt", "tau", "piv", "rank")])
+    for o in outs[1:]:
+        for x, y in zip(outs[0], o):
+            assert np.array_equal(x, y)

@@ -328,11 +328,15 @@ inline cudaError_t launch_gemm(const GemmParams& p, int batch, cudaStream_t st) 
                          : (ISDF_GEMM_SMALL ? (REAL_ONLY ? 64 : ISDF_GEMM_4M_BN) : BN_);
   using S = GemmSmem<BM, BN, A_KSLOW, B_KSLOW, gemm_bk(REAL_ONLY)>;
   auto kern = gemm_c128_kernel<BM, BN, A_KSLOW, B_KSLOW, MODE, REAL_ONLY, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in above 48 KB is a per-device attribute: remember it per device, not per process
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t eg = cudaGetDevice(&dev);
+  if (eg != cudaSuccess) return eg;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch * (p.ksplit > 1 ? p.ksplit : 1));

@@ -709,6 +709,10 @@ extern "C" int isdf_trsm_prepare(void* hv, const void* u, int ldu_rows, const in
 // One block row of a sweep: 64 x 32 tiles for full 64-row blocks, the transposed 32 x 64 tile for a ragged tail
 // of <= 32 live rows (every warp of the CTA then has live rows).
 static cudaError_t sweep_launch(const GemmParams& p, int batch, cudaStream_t st) {
+  // the sweeps update T in place (C rows alias B rows): race-free only while ONE M-tile covers the whole 64-row
+  // block (32 rows for the ragged tail, which takes the transposed tile)
+  static_assert(!gemm_is_3m(false) || (ISDF_GEMM_3M_BM >= TB && ISDF_GEMM_3M_BN >= 32), "sweep tile must cover a block row");
+  static_assert(gemm_is_3m(false) || ISDF_GEMM_SMALL, "in-place sweeps need the 64-row tile");
   if (p.M <= 32) return launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, st);
   return launch_gemm<128, 64, false, true, MODE_AB, false, EPI_STORE>(p, batch, st);
 }

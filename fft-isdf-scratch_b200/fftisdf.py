@@ -135,9 +135,15 @@ def build(df_obj):
     df_obj._host_cache = {}
 
     def mark(name):
+        # stage boundary: CUDA event (df_obj._stage_ms) + NVTX range, at the three places the reference puts its
+        # log.timer calls (fftisdf.py:386 selection, :89 "building y", :122 per-q) and the finer stages between them
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         ev[name] = e
+        if name != "start":
+            torch.cuda.nvtx.range_pop()
+        if name != "end":
+            torch.cuda.nvtx.range_push("isdf.build:after_" + name)
 
     mark("start")
     # Host AO table of the dense grid: start its (pinned, per-k) upload on a side stream now, so that it

@@ -464,8 +464,12 @@ class IsdfOps:
 
     def fft3d(self, data, mesh, pre=None, post=None, group_vecs=0, nvec=None, ldv=None, mode="auto"):
         """data: [..., ldv] rows of length prod(mesh) (row pitch ldv), transformed in place.
-        mode: "stockham" (shared-memory Stockham FFT), "dmma" (tensor-core dense DFT, axes <= 48) or
-        "auto" (dmma whenever every axis is in [2, 48]: measured faster than Stockham on all such meshes)."""
+        mode: "stockham" (shared-memory Stockham FFT with hard-coded radix-2/3/4/5/7/8/11/13 butterflies),
+        "dmma" (tensor-core dense DFT, axes <= 48) or "auto", by measurement (tools/fft_bench.py, profiles/):
+        Stockham when every axis factors into primes <= 13 and some axis is longer than 32 (33^3: 3.6 vs 4.2 ms,
+        45^3: 2.9 vs 4.4, 48^3: 2.9 vs 4.1), the tensor-core DFT for the other meshes with every axis in [2, 48]
+        (short axes, and lengths such as 31, 37, 41, where an FFT is an O(n^2) DFT anyway: 37^3 4.1 vs 28 ms), Stockham
+        with its direct-DFT stage for whatever is left."""
         assert data.is_cuda and data.dtype == c128 and data.stride(-1) == 1
         ng = int(np.prod(mesh))
         if ldv is None:
@@ -475,7 +479,8 @@ class IsdfOps:
         m = (C.c_int * 3)(*[int(x) for x in mesh])
         fits = all(2 <= int(x) <= 48 for x in mesh)
         if mode == "auto":
-            mode = "dmma" if fits else "stockham"
+            smooth = all(self._max_prime_factor(int(x)) <= 13 for x in mesh)
+            mode = "stockham" if ((smooth and max(int(x) for x in mesh) > 32) or not fits) else "dmma"
         if mode == "dmma":
             assert fits, "dmma DFT needs every mesh axis in [2, 48]"
             self.handle.check(self.lib.isdf_dft3d_dmma(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
@@ -485,7 +490,7 @@ class IsdfOps:
         self.handle.check(self.lib.isdf_fft3d_batched(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
                                                       int(group_vecs), _stream()), "isdf_fft3d_batched")
         gv = group_vecs if group_vecs > 0 else max(1, int(48 * 1024 * 1024 / (ng * 16)))
-        self.launches += 3 * (-(-nvec // gv))
+        self.launches += 2 * (-(-nvec // gv))
 
     def dft3d_p2p(self, peer_ptrs, ncol, row0, work, nvec, mesh, pre=None, post=None):
         """Tensor-core DFT with the all-to-all exchanges fused over NVLink peer memory (see the C header)."""

@@ -218,6 +218,25 @@ def test_fft3d(ops, mesh):
     assert relerr(d.cpu().numpy(), ref) < 1e-13
 
 
+@pytest.mark.parametrize("mesh", [[33, 33, 33], [15, 15, 15], [64, 64, 16], [8, 96, 96], [48, 40, 27], [17, 19, 23],
+                                  [37, 37, 3], [2, 3, 1], [1, 35, 1], [5, 1, 26], [13, 11, 7], [100, 4, 6]])
+def test_fft3d_stockham_kernels(ops, mesh):
+    """The shared-memory Stockham path on its own: every hard-coded radix (2,3,4,5,7,8,11,13), the direct-DFT stage for
+    larger primes, fused planes and the unfused fallback (96 x 96 plane), degenerate axes, a padded vector pitch."""
+    rng = np.random.default_rng(21)
+    ng = int(np.prod(mesh))
+    nvec, ldv = 3, ng + 3
+    x = crand(rng, nvec, ldv)
+    pre = np.exp(1j * rng.uniform(0, 6.28, ng))
+    post = rng.uniform(0.1, 2.0, ng)
+    d = dev(x.copy())
+    ops.fft3d(d, mesh, pre=dev(pre), post=dev(post), nvec=nvec, ldv=ldv, mode="stockham", group_vecs=2)
+    got = d.cpu().numpy()
+    ref = np.fft.fftn((x[:, :ng] * pre).reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng) * post
+    assert relerr(got[:, :ng], ref) < 1e-13
+    assert np.array_equal(got[:, ng:], x[:, ng:])          # padding untouched
+
+
 def test_gather_and_conj(ops):
     rng = np.random.default_rng(12)
     src = crand(rng, 2, 11, 301)

@@ -38,6 +38,10 @@ struct GemmParams {
   const int* perm; long stridePerm;  // EPI_HERK: optional row/col scatter map per batch
   const int* active;                 // optional per-batch flag; batch skipped when 0
   int ksplit; int kchunk; long strideSplit;  // split-K: grid.z = batch*ksplit, partial results at C + ks*strideSplit
+  // L2 rasterisation (plain EPI_STORE products only): CTAs are dealt in groups of group_m consecutive M-tiles per
+  // N-tile, so that a B column panel fetched from DRAM is shared by group_m resident CTAs instead of being re-read for
+  // every M-tile (ncu on the NiO fit GEMM: 1.23 TB of DRAM reads per launch for 32 GB of operands without it)
+  int group_m = 0;
 };
 
 #ifndef ISDF_GEMM_BK
@@ -119,7 +123,17 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN, REAL_ONLY), gemm_min_bloc
   int ksp = 0;
   if (p.ksplit > 1) { ksp = bz % p.ksplit; bz /= p.ksplit; }
   if (p.active != nullptr && p.active[bz] == 0) return;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  if (!SYMM && p.group_m > 1) {
+    const long id = (long)blockIdx.y * gridDim.x + blockIdx.x;
+    const long per = (long)p.group_m * gridDim.x;
+    const int g0 = (int)(id / per) * p.group_m;
+    const int rows = min(p.group_m, (int)gridDim.y - g0);
+    const long r = id - (long)(id / per) * per;
+    tile_y = g0 + (int)(r % rows);
+    tile_x = (int)(r / rows);
+  }
+  const int m0 = tile_y * BM, n0 = tile_x * BN;
   if (SYMM && n0 >= m0 + BM) return;  // tile strictly above the diagonal: produced by mirroring
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

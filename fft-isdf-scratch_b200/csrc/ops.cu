@@ -238,6 +238,7 @@ extern "C" int isdf_gemm_nn(void* hv, const void* a, long lda, long strideA, con
   p.M = m; p.N = n; p.K = k;
   p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
   p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
+  p.group_m = (m >= 512 && (long)n * k * 16 > (64L << 20)) ? 16 : 0;   // B panel larger than L2's share: rasterise
   ISDF_CUDA(h, (launch_gemm<64, 128, false, true, MODE_AB, false, EPI_STORE>(p, batch, (cudaStream_t)stream)));
   return ISDF_OK;
 }

@@ -429,6 +429,93 @@ __global__ void pchol_finalize_kernel(const int* pos, const PcholInfo* info, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Blocked UNPIVOTED Cholesky A = U^H U (right-looking, 64-wide block columns) for the well-conditioned Gram matrices of
+// the Cholesky-QR step: per block one CTA factorises the 64 x 64 diagonal block in shared memory (A_jj = L L^H,
+// U_jj = L^H) and inverts L; the block row U_j,rest = L^-1 A_j,rest and the trailing update run on the GEMM engine.
+// Stops at the first pivot <= tol (rows of an exactly singular trailing block: rank < n), like the pivoted kernels.
+constexpr int CB = 64;
+__global__ void __launch_bounds__(256) chol_diag_kernel(const cplx* __restrict__ Aall, long strideA, int n, int j0,
+                                                        double tol, cplx* __restrict__ Uall, long strideU,
+                                                        cplx* __restrict__ Winv, PcholInfo* infoall, int* active) {
+  const int b = blockIdx.x;
+  PcholInfo* info = infoall + b;
+  cplx* W = Winv + (long)b * CB * CB;
+  const int tid = threadIdx.x;
+  const int nb = min(CB, n - j0);
+  if (info->done) {
+    for (int e = tid; e < CB * CB; e += 256) W[e] = make_double2(0.0, 0.0);
+    return;
+  }
+  extern __shared__ __align__(16) unsigned char cd_smem[];
+  cplx* S = reinterpret_cast<cplx*>(cd_smem);       // [CB][CB+1]  lower triangle: L
+  cplx* X = S + CB * (CB + 1);                      // [CB][CB+1]  L^-1
+  __shared__ int s_stop;
+  const cplx* A = Aall + (long)b * strideA + (long)j0 * n + j0;
+  for (int e = tid; e < CB * CB; e += 256) {
+    const int r = e / CB, c = e - r * CB;
+    S[r * (CB + 1) + c] = (r < nb && c <= r) ? A[(long)r * n + c] : make_double2(0.0, 0.0);
+    X[r * (CB + 1) + c] = make_double2(0.0, 0.0);
+  }
+  if (tid == 0) s_stop = nb;
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {
+    const double d = S[k * (CB + 1) + k].x;
+    if (!(d > tol) || !(d > 0.0)) { if (tid == 0) s_stop = k; break; }       // uniform: d comes from shared memory
+    const double lkk = sqrt(d), inv = 1.0 / lkk;
+    __syncthreads();
+    for (int i = k + tid; i < nb; i += 256) {
+      cplx v = S[i * (CB + 1) + k];
+      S[i * (CB + 1) + k] = (i == k) ? make_double2(lkk, 0.0) : make_double2(v.x * inv, v.y * inv);
+    }
+    __syncthreads();
+    // trailing lower triangle: S[i][c] -= L[i][k] conj(L[c][k]),  i >= c > k
+    const int m = nb - k - 1;
+    for (int e = tid; e < m * m; e += 256) {
+      const int i = k + 1 + e / m, c = k + 1 + e % m;
+      if (c <= i) {
+        const cplx li = S[i * (CB + 1) + k], lc = S[c * (CB + 1) + k];
+        cplx v = S[i * (CB + 1) + c];
+        v.x -= li.x * lc.x + li.y * lc.y;
+        v.y -= li.y * lc.x - li.x * lc.y;
+        S[i * (CB + 1) + c] = v;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const int kk = s_stop;                              // leading kk x kk block is factorised
+  // X = L^-1 (lower), one column per thread by forward substitution
+  if (tid < kk) {
+    const int c = tid;
+    for (int i = c; i < kk; ++i) {
+      cplx acc = make_double2((i == c) ? 1.0 : 0.0, 0.0);
+      for (int k = c; k < i; ++k) {
+        const cplx l = S[i * (CB + 1) + k], x = X[k * (CB + 1) + c];
+        acc.x -= l.x * x.x - l.y * x.y;
+        acc.y -= l.x * x.y + l.y * x.x;
+      }
+      const double dinv = 1.0 / S[i * (CB + 1) + i].x;
+      X[i * (CB + 1) + c] = make_double2(acc.x * dinv, acc.y * dinv);
+    }
+  }
+  __syncthreads();
+  cplx* U = Uall + (long)b * strideU + (long)j0 * n + j0;
+  for (int e = tid; e < CB * CB; e += 256) {
+    const int r = e / CB, c = e - r * CB;
+    W[e] = (r < kk && c <= r) ? X[r * (CB + 1) + c] : make_double2(0.0, 0.0);
+    if (r < nb && c < nb) {
+      cplx u = make_double2(0.0, 0.0);
+      if (r < kk && c >= r) { const cplx l = S[c * (CB + 1) + r]; u = make_double2(l.x, -l.y); }   // U_jj = L^H
+      U[(long)r * n + c] = u;
+    }
+  }
+  if (tid == 0) {
+    if (kk < nb) { info->rank = j0 + kk; info->done = 1; active[b] = 0; }
+    else info->rank = j0 + nb;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Triangular-sweep operator construction.
 // Up[a][b] = U[a][piv[b]] for a<=b<rank, identity on [rank, nP); Lp = Up^H.
 __global__ void build_up_lp_kernel(const cplx* Uall, long ldu, long strideU, const int* pivall, const int* rank, int n,
@@ -585,13 +672,66 @@ extern "C" int isdf_pchol_real(void* hv, void* a, int n, int batch, int max_step
                    true);
 }
 
-// Unpivoted Cholesky A = U^H U through the same kernels (pivot = next position): used by the Cholesky-QR that
-// orthonormalises the rows of the scaled [R11 R12] factor of the gelsy fit (fftisdf.py:108).  Stops at the first
-// pivot <= tol (tol = 0: an exactly singular trailing block).
+// Unpivoted blocked Cholesky A = U^H U of [batch][n][n] Hermitian matrices (lower triangle read and destroyed): used by
+// the Cholesky-QR that orthonormalises the rows of the scaled [R11 R12] factor of the gelsy fit (fftisdf.py:108).
+// Stops at the first pivot <= tol (tol = 0: an exactly singular trailing block).  u [batch][ldu_rows >= n][n] upper
+// triangular (rows >= rank zero), piv = identity, rank [batch].  workspace: isdf_pchol_workspace_bytes(n, batch) +
+// batch * 64 * 64 * 16 bytes.
 extern "C" int isdf_chol_nopivot(void* hv, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
                                  int ldu_rows, int* piv, int* rank, void* workspace, void* stream) {
-  return pchol_run((Handle*)hv, a, n, batch, max_steps, tol, nb, u, ldu_rows, piv, rank, nullptr, workspace, stream,
-                   false, 1);
+  Handle* h = (Handle*)hv;
+  cudaStream_t st = (cudaStream_t)stream;
+  (void)nb;
+  ISDF_CHECK_ARG(h, a && u && piv && rank && workspace, "null pointer");
+  ISDF_CHECK_ARG(h, n >= 1 && batch >= 1 && batch <= 65535 && max_steps == n && ldu_rows >= n, "shape");
+  char* w = (char*)workspace;
+  int* pos = (int*)w;
+  size_t off = ((size_t)n * batch * sizeof(int) + 255) / 256 * 256;
+  PcholInfo* info = (PcholInfo*)(w + off);
+  off += ((size_t)batch * sizeof(PcholInfo) + 255) / 256 * 256;
+  int* active = (int*)(w + off);
+  off += ((size_t)batch * sizeof(int) + 255) / 256 * 256;
+  cplx* winv = (cplx*)(w + off);
+  const long strideA = (long)n * n, strideU = (long)ldu_rows * n;
+  ISDF_CUDA(h, cudaMemsetAsync(u, 0, (size_t)batch * ldu_rows * n * sizeof(cplx), st));
+  {
+    const long tot = (long)n * batch;
+    pchol_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pos, info, active, n, batch);
+    ISDF_LAUNCH_CHECK(h);
+  }
+  const size_t sm = 2 * CB * (CB + 1) * sizeof(cplx);
+  ISDF_CUDA(h, cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  for (int j0 = 0; j0 < n; j0 += CB) {
+    const int jb = (n - j0 < CB) ? (n - j0) : CB;
+    chol_diag_kernel<<<batch, 256, sm, st>>>((const cplx*)a, strideA, n, j0, tol, (cplx*)u, strideU, winv, info, active);
+    ISDF_LAUNCH_CHECK(h);
+    const int rest = n - j0 - jb;
+    if (rest <= 0) break;
+    GemmParams p;
+    // block row: U[j0 + r][c] = sum_k Linv[r][k] conj(A[c][j0 + k]),  c > j0 + jb   (A_j,c = conj(A_c,j): lower storage)
+    p.A = winv; p.lda = CB; p.strideA = (long)CB * CB;
+    p.B = (const cplx*)a + (long)(j0 + jb) * n + j0; p.ldb = n; p.strideB = strideA;
+    p.C = (cplx*)u + (long)j0 * n + (j0 + jb); p.ldc = n; p.strideC = strideU;
+    p.M = jb; p.N = rest; p.K = jb;
+    p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+    p.perm = nullptr; p.stridePerm = 0; p.active = active; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
+    ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_STORE>(p, batch, st)));
+    // trailing update (lower triangle): A[c][c'] -= sum_r conj(U[r][c]) U[r][c'],  c, c' > j0 + jb
+    GemmParams q;
+    q.A = (const cplx*)u + (long)j0 * n + (j0 + jb); q.lda = n; q.strideA = strideU;
+    q.B = q.A; q.ldb = n; q.strideB = strideU;
+    q.C = (cplx*)a + (long)(j0 + jb) * n + (j0 + jb); q.ldc = n; q.strideC = strideA;
+    q.M = rest; q.N = rest; q.K = jb;
+    q.nseg = 1; q.segA = 0; q.segB = 0; q.alpha = 1.0;
+    q.perm = nullptr; q.stridePerm = 0; q.active = active; q.ksplit = 1; q.kchunk = 0; q.strideSplit = 0;
+    ISDF_CUDA(h, (launch_gemm<128, 64, true, true, MODE_CONJA, false, EPI_SUB_LOWER>(q, batch, st)));
+  }
+  {
+    const long tot = (long)n * batch;
+    pchol_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pos, info, n, batch, piv, rank, nullptr);
+    ISDF_LAUNCH_CHECK(h);
+  }
+  return ISDF_OK;
 }
 
 static int pchol_run(Handle* h, void* a, int n, int batch, int max_steps, double tol, int nb, void* u, int ldu_rows,

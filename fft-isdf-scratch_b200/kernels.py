@@ -273,11 +273,11 @@ class IsdfOps:
         rank = torch.empty((batch,), dtype=torch.int32, device=self.device)
         nbytes = C.c_size_t()
         self.lib.isdf_pchol_workspace_bytes(n, batch, C.byref(nbytes))
-        work = torch.empty((nbytes.value,), dtype=torch.uint8, device=self.device)
+        work = torch.empty((nbytes.value + batch * 64 * 64 * 16,), dtype=torch.uint8, device=self.device)
         self.handle.check(self.lib.isdf_chol_nopivot(self.h, _ptr(a), n, batch, n, float(tol), int(nb), _ptr(u), n,
                                                      _ptr(piv), _ptr(rank), _ptr(work), _stream()),
                           "isdf_chol_nopivot")
-        self.launches += 3 + 2 * max(1, -(-n // nb))
+        self.launches += 2 + 3 * (-(-n // 64))
         return u, piv, rank
 
     # ---- K5 (reference semantics): LAPACK zgelsy restated on the device (fftisdf.py:108) ---------------

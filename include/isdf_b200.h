@@ -135,8 +135,10 @@ int isdf_trsm_sweeps(void* handle, const void* lfwd, const void* ubwd, void* t, 
 /* One direction of the above: backward = 0: T <- U^{-H} T with op = lfwd; backward = 1: T <- U^{-1} T with op = ubwd. */
 int isdf_trsm_sweep(void* handle, const void* op, void* t, int nP, int nact, long ng, long ldt, int batch,
                     int backward, void* stream);
-/* Unpivoted Cholesky A = U^H U (same kernels and argument meaning as isdf_pchol, pivot = next position; piv
- * comes back as the identity).  Stops at the first pivot <= tol. */
+/* Unpivoted blocked Cholesky A = U^H U (64-wide block columns: diagonal block in shared memory, block row and
+ * trailing update on the GEMM engine); argument meaning as isdf_pchol with max_steps = n, piv comes back as the
+ * identity.  Stops at the first pivot <= tol (rank < n).  workspace: isdf_pchol_workspace_bytes(n, batch) +
+ * batch * 64 * 64 * 16 bytes. */
 int isdf_chol_nopivot(void* handle, void* a, int n, int batch, int max_steps, double tol, int nb, void* u,
                       int ldu_rows, int* piv, int* rank, void* workspace, void* stream);
 

@@ -156,3 +156,22 @@ def test_qrcp_is_bit_identical_for_every_cluster_size(n):
     for o in outs[1:]:
         for x, y in zip(outs[0], o):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("n,r", [(64, 64), (100, 100), (200, 131), (448, 448), (130, 64)])
+def test_blocked_unpivoted_cholesky(n, r):
+    """isdf_chol_nopivot (the Cholesky of the Cholesky-QR step): U^H U = A for well-conditioned Hermitian matrices, and a
+    clean stop at the first zero pivot when the trailing rows/columns are exactly zero (rank < n)."""
+    ops = _ops()
+    rng = np.random.default_rng(n + r)
+    c = rng.standard_normal((2, r + 20, r)) + 1j * rng.standard_normal((2, r + 20, r))
+    a = np.zeros((2, n, n), dtype=complex)
+    a[:, :r, :r] = np.einsum("bki,bkj->bij", c.conj(), c) / (r + 20)
+    u, piv, rank = ops.chol_nopivot(_dev(a))
+    u, rank = u.cpu().numpy(), rank.cpu().numpy()
+    assert rank.tolist() == [r, r] and np.array_equal(piv.cpu().numpy()[0], np.arange(n))
+    for z in range(2):
+        assert np.abs(np.tril(u[z], -1)).max() == 0.0 and (r == n or np.abs(u[z][r:]).max() == 0.0)
+        assert np.abs(u[z].conj().T @ u[z] - a[z]).max() < 1e-13 * np.abs(a[z]).max()
+        ref = np.linalg.cholesky(a[z][:r, :r]).conj().T
+        assert np.abs(u[z][:r, :r] - ref).max() < 1e-12 * np.abs(ref).max()

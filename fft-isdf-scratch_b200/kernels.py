@@ -355,7 +355,7 @@ class IsdfOps:
              eh   [batch, rP, n]   E^H (orthonormal rows, zero beyond rank; E = P Z1^H of ztzrzf/zunmrz)
            so that  Theta~ = G Y^T  [rank x ng],  Theta = eh^H Theta~  and  W = eh^H W~ eh.
            D = |diag R|;  D^-1 [R11 R12] P^T = U^H E^H by Cholesky-QR (twice) with U upper triangular.
-           debug=True also returns q1s [batch, n, rP] = Q1 D^-1 and lfwd (the block operator of U^-H)."""
+           debug=True also returns q1s [batch, n, rP] = Q1 D^-1 and lfwd (the block operators of U1^-H, U2^-H; U = U2 U1)."""
         w, vt, tau, piv, pos, rank = st["w"], st["vt"], st["tau"], st["piv"], st["pos"], st["rank"]
         batch, n, _ = w.shape
         assert rP % TB == 0
@@ -398,7 +398,7 @@ class IsdfOps:
         self.handle.check(self.lib.isdf_gelsy_rhat(self.h, _ptr(w), _ptr(pos), _ptr(dinv), _ptr(rank), n, rP, batch,
                                                    _ptr(eh), _stream()), "isdf_gelsy_rhat")
         self.launches += 1
-        us = []
+        lfs = []
         for _ in range(2):
             with self.timed("ops_cholqr_herk"):
                 gg = self.herk(eh)
@@ -407,16 +407,15 @@ class IsdfOps:
             with self.timed("ops_cholqr_solve"):
                 lf, _ = self.trsm_prepare(u, ident, rk, rP)
                 self.trsm_sweep(lf, eh, backward=False)
-            us.append(u)
-            del gg, lf
+            lfs.append(lf)
+            del gg, u
         with self.timed("ops_g"):
-            ucomb = self.gemm_nn(us[1], us[0])                                # U = U2 U1
-            del us
-            lfwd, _ = self.trsm_prepare(ucomb, ident, rank, rP)
-            self.trsm_sweep(lfwd, gt, backward=False)                         # G = U^-H (D^-1 Q1^H)
+            # G = U^-H (D^-1 Q1^H) with U = U2 U1:  U^-H = U2^-H U1^-H, applied as the two substitutions already set up
+            self.trsm_sweep(lfs[0], gt, backward=False)
+            self.trsm_sweep(lfs[1], gt, backward=False)
         out.update(gt=gt, eh=eh, chol_rank=rk)
         if debug:
-            out["lfwd"] = lfwd
+            out["lfwd"] = lfs
         return out
 
     def gemm_nn_strided(self, a, b, out):

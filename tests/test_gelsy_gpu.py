@@ -119,7 +119,8 @@ def test_gelsy_operators_and_solution(n, r, decay, seed):
     c = ops.gemm_hn(fac["q1s"], bt)                                        # [2, rP, 9]
     cpad = torch.zeros((2, rP, 64), dtype=torch.complex128, device=c.device)
     cpad[:, :, :9] = c
-    ops.trsm_sweep(fac["lfwd"], cpad, nact=int(rank.max()), backward=False, ng=9)
+    for lf in fac["lfwd"]:                                                  # U^-H = U2^-H U1^-H
+        ops.trsm_sweep(lf, cpad, nact=int(rank.max()), backward=False, ng=9)
     x2 = ops.gemm_hn(fac["eh"], cpad.contiguous())[:, :, :9].cpu().numpy()
     # ... and the fused operator the build uses:  x = E (G b),  G = U^-H D^-1 Q1^H
     x = ops.gemm_hn(fac["eh"], ops.gemm_nn(fac["gt"], bt)).cpu().numpy()

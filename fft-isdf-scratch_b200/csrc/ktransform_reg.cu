@@ -73,17 +73,31 @@ __device__ __forceinline__ void dft_axis_real_in(cplx (&x)[NK]) {
   }
 }
 
+// Columns per thread: tiny k-meshes (nk <= 4, e.g. the Gamma point, where the "transform" is just the square) leave a
+// thread with one or two 16-byte loads in flight -- the stage is then latency-bound at ~0.1 of the HBM rate; several
+// independent column chunks per thread restore the memory-level parallelism.
+__host__ __device__ constexpr int kt_cpt(int nk) { return nk >= 8 ? 1 : (nk >= 4 ? 2 : (nk >= 2 ? 4 : 8)); }
+
 template <int N1, int N2, int N3>
 __global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
   constexpr int NK = N1 * N2 * N3;
-  const int c = blockIdx.x * 128 + threadIdx.x;
+  constexpr int CPT = kt_cpt(NK);
   const int r = blockIdx.y;
   double mx_im = 0.0, mx_re = 0.0;
-  if (c < p.ncols) {
-    cplx x[NK];
+  // all loads first (the stores below may alias the input as far as the compiler knows)
+  cplx xs[CPT][NK];
+#pragma unroll
+  for (int cu = 0; cu < CPT; ++cu) {
+    const int c = (blockIdx.x * CPT + cu) * 128 + threadIdx.x;
     const cplx* src = p.in + (long)r * p.in_sr + c;
 #pragma unroll
-    for (int k = 0; k < NK; ++k) x[k] = src[(long)k * p.in_sk];
+    for (int k = 0; k < NK; ++k) xs[cu][k] = (c < p.ncols) ? src[(long)k * p.in_sk] : make_double2(0.0, 0.0);
+  }
+#pragma unroll
+  for (int cu = 0; cu < CPT; ++cu) {
+  const int c = (blockIdx.x * CPT + cu) * 128 + threadIdx.x;
+  if (c < p.ncols) {
+    cplx (&x)[NK] = xs[cu];
     dft_axis<N3, 1, NK, 2, false>(x);
     dft_axis<N2, N3, NK, 1, false>(x);
     dft_axis<N1, N2 * N3, NK, 0, false>(x);
@@ -119,6 +133,7 @@ __global__ void __launch_bounds__(128) ktransform_reg_kernel(KtRegParams p) {
       }
       p.out[(long)slot * p.out_sq + (long)row * p.out_sr + p.out_c0 + c] = x[q];
     }
+  }
   }
   if (p.diag != nullptr) {
 #pragma unroll
@@ -246,7 +261,8 @@ static cudaError_t launch_split(const KtRegParams& p, cudaStream_t st) {
 
 template <int N1, int N2, int N3>
 static cudaError_t launch_reg(const KtRegParams& p, cudaStream_t st) {
-  dim3 grid((p.ncols + 127) / 128, p.nrows);
+  constexpr int CPT = kt_cpt(N1 * N2 * N3);
+  dim3 grid((p.ncols + 128 * CPT - 1) / (128 * CPT), p.nrows);
   ktransform_reg_kernel<N1, N2, N3><<<grid, 128, 0, st>>>(p);
   return cudaGetLastError();
 }

@@ -71,6 +71,10 @@ SIGNATURES = {
                            c_long, c_long, c_double, c_void_p],
     "isdf_fft3d_batched": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_long, c_void_p],
     "isdf_fft_release_plans": [c_void_p],
+    "isdf_fft3d_reg_supported": [P_int],
+    "isdf_fft3d_reg": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_long, c_void_p],
+    "isdf_fft3d_reg_p2p": [c_void_p, C.POINTER(c_void_p), c_int, c_long, c_long, c_void_p, c_long, c_long, P_int,
+                           c_void_p, c_void_p, c_void_p],
     "isdf_dft3d_dmma": [c_void_p, c_void_p, c_long, c_long, P_int, c_void_p, c_void_p, c_void_p],
     "isdf_dft3d_dmma_p2p": [c_void_p, C.POINTER(c_void_p), c_int, c_long, c_long, c_void_p, c_long, c_long, P_int,
                             c_void_p, c_void_p, c_void_p],

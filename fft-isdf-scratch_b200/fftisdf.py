@@ -287,7 +287,8 @@ def build(df_obj):
     _log(df_obj, "nkpt = %d, ngrid = %d, nip = %d", nkpt, ngrid, nip)
     # Y^T, then Theta, then B (in place).  Multi-GPU with a tensor-core-DFT mesh: the buffer lives in NVLink
     # peer-mapped memory so that the FFT kernels gather/scatter it directly (no all-to-all, no permute copies).
-    p2p = world > 1 and all(2 <= m <= 48 for m in mesh) and getattr(df_obj, "exchange", "p2p") == "p2p"
+    p2p = (world > 1 and getattr(df_obj, "exchange", "p2p") == "p2p"
+           and (all(2 <= m <= 48 for m in mesh) or (ops.fft3d_reg_supported(mesh) and mesh[0] > 1)))
     # Memory guard (the reference raises RuntimeError on a shortfall, fftdf-with-k.py:41-48): the one O(nq nip ng)
     # object is Theta; the per-block scratch (fx^T for all k, Y^T for all q) is sized to what is left.
     blksize = int(df_obj.blksize)

@@ -461,14 +461,19 @@ class IsdfOps:
                 p += 1
         return f
 
+    def fft3d_reg_supported(self, mesh):
+        """True when the register-resident FFT kernels (fft_reg.cu) have an instantiation for this mesh."""
+        m = (C.c_int * 3)(*[int(x) for x in mesh])
+        return bool(self.lib.isdf_fft3d_reg_supported(m))
+
     def fft3d(self, data, mesh, pre=None, post=None, group_vecs=0, nvec=None, ldv=None, mode="auto"):
         """data: [..., ldv] rows of length prod(mesh) (row pitch ldv), transformed in place.
-        mode: "stockham" (shared-memory Stockham FFT with hard-coded radix-2/3/4/5/7/8/11/13 butterflies),
-        "dmma" (tensor-core dense DFT, axes <= 48) or "auto", by measurement (tools/fft_bench.py, profiles/):
-        Stockham when every axis factors into primes <= 13 and some axis is longer than 32 (33^3: 3.6 vs 4.2 ms,
-        45^3: 2.9 vs 4.4, 48^3: 2.9 vs 4.1), the tensor-core DFT for the other meshes with every axis in [2, 48]
-        (short axes, and lengths such as 31, 37, 41, where an FFT is an O(n^2) DFT anyway: 37^3 4.1 vs 28 ms), Stockham
-        with its direct-DFT stage for whatever is left."""
+        mode: "reg" (register-resident two-factor / direct-prime kernels with compile-time axis lengths: one
+        shared-memory exchange per axis, every element read and written once per pass), "stockham" (generic
+        shared-memory Stockham FFT, any mesh), "dmma" (tensor-core dense DFT, axes <= 48) or "auto": "reg" when the
+        mesh is instantiated, else the round-1 routing by measurement (Stockham when every axis factors into primes
+        <= 13 and some axis is longer than 32, the tensor-core DFT for the other meshes with every axis in [2, 48],
+        Stockham with its direct-DFT stage for whatever is left)."""
         assert data.is_cuda and data.dtype == c128 and data.stride(-1) == 1
         ng = int(np.prod(mesh))
         if ldv is None:
@@ -478,8 +483,17 @@ class IsdfOps:
         m = (C.c_int * 3)(*[int(x) for x in mesh])
         fits = all(2 <= int(x) <= 48 for x in mesh)
         if mode == "auto":
-            smooth = all(self._max_prime_factor(int(x)) <= 13 for x in mesh)
-            mode = "stockham" if ((smooth and max(int(x) for x in mesh) > 32) or not fits) else "dmma"
+            if self.lib.isdf_fft3d_reg_supported(m):
+                mode = "reg"
+            else:
+                smooth = all(self._max_prime_factor(int(x)) <= 13 for x in mesh)
+                mode = "stockham" if ((smooth and max(int(x) for x in mesh) > 32) or not fits) else "dmma"
+        if mode == "reg":
+            self.handle.check(self.lib.isdf_fft3d_reg(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
+                                                      int(group_vecs), _stream()), "isdf_fft3d_reg")
+            ngroups = 1 if group_vecs <= 0 else -(-nvec // int(group_vecs))
+            self.launches += (2 if int(mesh[0]) > 1 else 1) * ngroups if nvec > 0 else 0
+            return
         if mode == "dmma":
             assert fits, "dmma DFT needs every mesh axis in [2, 48]"
             self.handle.check(self.lib.isdf_dft3d_dmma(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
@@ -491,14 +505,18 @@ class IsdfOps:
         gv = group_vecs if group_vecs > 0 else max(1, int(48 * 1024 * 1024 / (ng * 16)))
         self.launches += 2 * (-(-nvec // gv))
 
-    def dft3d_p2p(self, peer_ptrs, ncol, row0, work, nvec, mesh, pre=None, post=None):
-        """Tensor-core DFT with the all-to-all exchanges fused over NVLink peer memory (see the C header)."""
+    def dft3d_p2p(self, peer_ptrs, ncol, row0, work, nvec, mesh, pre=None, post=None, mode="auto"):
+        """3-D transform with the all-to-all exchanges fused over NVLink peer memory (see the C header): the
+        register-resident FFT kernels when the mesh is instantiated ("reg"), else the tensor-core DFT ("dmma")."""
         world = len(peer_ptrs)
         arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
         m = (C.c_int * 3)(*[int(x) for x in mesh])
-        self.handle.check(self.lib.isdf_dft3d_dmma_p2p(self.h, arr, world, int(ncol), int(row0), _ptr(work), int(nvec),
-                                                       work.shape[-1], m, _ptr(pre), _ptr(post), _stream()),
-                          "isdf_dft3d_dmma_p2p")
+        if mode == "auto":
+            mode = "reg" if (self.lib.isdf_fft3d_reg_supported(m) and int(mesh[0]) > 1) else "dmma"
+        fn, name = ((self.lib.isdf_fft3d_reg_p2p, "isdf_fft3d_reg_p2p") if mode == "reg"
+                    else (self.lib.isdf_dft3d_dmma_p2p, "isdf_dft3d_dmma_p2p"))
+        self.handle.check(fn(self.h, arr, world, int(ncol), int(row0), _ptr(work), int(nvec), work.shape[-1], m,
+                             _ptr(pre), _ptr(post), _stream()), name)
         self.launches += 2 if nvec > 0 else 0
 
     # ---- K7: W = alpha * B B^H, scattered through perm -------------------------------------------

@@ -182,6 +182,14 @@ int isdf_gemm_tn(void* handle, const void* a, long lda, long strideA, const void
 int isdf_fft3d_batched(void* handle, void* data, long nvec, long ldv, const int* mesh, const void* pre,
                        const double* post, long group_vecs, void* stream);
 int isdf_fft_release_plans(void* handle);
+/* Same contract, register-resident kernels with compile-time axis lengths (fft_reg.cu): two-factor lengths
+ * N = R1 R2 (R1, R2 <= 16) and primes <= 61; a plane pass (z + y, in place in shared memory) and an x pass, each
+ * touching every element once.  isdf_fft3d_reg_supported(mesh) -> 1 when mesh[1] == mesh[2] and the lengths are
+ * instantiated; isdf_fft3d_reg returns -2 without launching otherwise (the host then keeps isdf_fft3d_batched /
+ * isdf_dft3d_dmma).  group_vecs > 0 runs both passes per group of vectors, <= 0 per batch. */
+int isdf_fft3d_reg_supported(const int* mesh);
+int isdf_fft3d_reg(void* handle, void* data, long nvec, long ldv, const int* mesh, const void* pre,
+                   const double* post, long group_vecs, void* stream);
 /* Same contract as isdf_fft3d_batched for meshes with every axis in [2, 48]: each 1-D transform is a dense
  * product with the n x n DFT matrix on the FP64 tensor pipe (for lengths with large prime factors, e.g. 31,
  * 37, 41).  Returns -2 without launching when an axis is out of range. */
@@ -195,6 +203,9 @@ int isdf_dft3d_dmma(void* handle, void* data, long nvec, long ldv, const int* me
  * (P2P stores).  The caller barriers across ranks before (shards complete) and after (scatter visible). */
 int isdf_dft3d_dmma_p2p(void* handle, void* const* peers, int world, long ncol, long row0, void* work, long nvec,
                         long ldv, const int* mesh, const void* pre, const double* post, void* stream);
+/* The same fused exchange for the register-resident FFT kernels (meshes isdf_fft3d_reg_supported accepts, n1 > 1). */
+int isdf_fft3d_reg_p2p(void* handle, void* const* peers, int world, long ncol, long row0, void* work, long nvec,
+                       long ldv, const int* mesh, const void* pre, const double* post, void* stream);
 
 /* Per-q tables of the Coulomb stage generated on the device:
  * fftisdf.py:114-115  get_coulG(cell, k=vq, mesh) (exxdiv=None, wrap_around=True) folded with vol/ngrid and

@@ -237,6 +237,46 @@ def test_fft3d_stockham_kernels(ops, mesh):
     assert np.array_equal(got[:, ng:], x[:, ng:])          # padding untouched
 
 
+@pytest.mark.parametrize("mesh", [[32, 32, 32], [33, 33, 33], [37, 37, 37], [48, 48, 48], [64, 64, 64], [15, 96, 96],
+                                  [1, 45, 45], [61, 17, 17], [108, 25, 25], [16, 105, 105], [27, 59, 59]])
+def test_fft3d_register_kernels(ops, mesh):
+    """Register-resident FFT (fft_reg.cu): two-factor lengths (in-place plane buffer, one exchange per axis), direct
+    symmetric DFT for primes, mixed x / plane lengths, a 2-D mesh, a padded vector pitch, ragged x tiles, groups."""
+    assert ops.fft3d_reg_supported(mesh)
+    rng = np.random.default_rng(31)
+    ng = int(np.prod(mesh))
+    nvec, ldv = 3, ng + 3
+    x = crand(rng, nvec, ldv)
+    pre = np.exp(1j * rng.uniform(0, 6.28, ng))
+    post = rng.uniform(0.1, 2.0, ng)
+    d = dev(x.copy())
+    ops.fft3d(d, mesh, pre=dev(pre), post=dev(post), nvec=nvec, ldv=ldv, mode="reg", group_vecs=2)
+    got = d.cpu().numpy()
+    ref = np.fft.fftn((x[:, :ng] * pre).reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng) * post
+    assert relerr(got[:, :ng], ref) < 1e-13
+    assert np.array_equal(got[:, ng:], x[:, ng:])          # padding untouched
+    d = dev(x.copy())
+    ops.fft3d(d, mesh, nvec=nvec, ldv=ldv)                 # auto routing picks the same kernels; no phase / weight
+    ref = np.fft.fftn(x[:, :ng].reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng)
+    assert relerr(d.cpu().numpy()[:, :ng], ref) < 1e-13
+
+
+def test_fft3d_register_kernels_every_length(ops):
+    """Every instantiated axis length once (n x n planes, x pass of the same length on a thin mesh)."""
+    rng = np.random.default_rng(32)
+    for n in range(15, 109):
+        if not ops.fft3d_reg_supported([1, n, n]):
+            continue
+        for mesh in ([1, n, n], [n, 15, 15]):
+            ng = int(np.prod(mesh))
+            x = crand(rng, 2, ng)
+            d = dev(x.copy())
+            ops.fft3d(d, mesh, mode="reg")
+            ref = np.fft.fftn(x.reshape(2, *mesh), axes=(1, 2, 3)).reshape(2, ng)
+            assert relerr(d.cpu().numpy(), ref) < 1e-13, mesh
+    assert not ops.fft3d_reg_supported([8, 64, 32]) and not ops.fft3d_reg_supported([4, 127, 127])
+
+
 def test_gather_and_conj(ops):
     rng = np.random.default_rng(12)
     src = crand(rng, 2, 11, 301)

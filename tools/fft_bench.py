@@ -8,8 +8,10 @@ for mesh, nvec in [([37] * 3, 448 * 4), ([33] * 3, 544 * 4), ([32] * 3, 2048), (
     x = torch.randn(nvec, ng, dtype=torch.complex128, device="cuda")
     pre = torch.randn(ng, dtype=torch.complex128, device="cuda")
     post = torch.rand(ng, dtype=torch.float64, device="cuda")
-    for mode in ["stockham", "dmma"]:
+    for mode in (sys.argv[1:] or ["reg", "stockham", "dmma"]):
         if mode == "dmma" and max(mesh) > 48:
+            continue
+        if mode == "reg" and not ops.fft3d_reg_supported(mesh):
             continue
         for _ in range(2):
             ops.fft3d(x, mesh, pre=pre, post=post, mode=mode)

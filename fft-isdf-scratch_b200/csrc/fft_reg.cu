@@ -28,6 +28,24 @@ static const RegPlan* find_plan(int n) {
   return nullptr;
 }
 
+// ticket / publication counters of the fused launch (device) and its sticky time-out flag (host-mapped), per device
+constexpr int FUSED_MAX_GROUPS = 1 << 16;
+struct FusedSync { int* sync; int* err_host; int* err_dev; };
+static FusedSync g_fsync[8];
+
+static int fused_sync(Handle* h, FusedSync** out) {
+  if (h->device < 0 || h->device >= 8) return ISDF_ESIZE;
+  FusedSync& f = g_fsync[h->device];
+  if (!f.sync) {
+    ISDF_CUDA(h, cudaMalloc(&f.sync, sizeof(int) * (FUSED_MAX_GROUPS + 1)));
+    ISDF_CUDA(h, cudaHostAlloc(&f.err_host, sizeof(int), cudaHostAllocMapped));
+    *f.err_host = 0;
+    ISDF_CUDA(h, cudaHostGetDevicePointer(&f.err_dev, f.err_host, 0));
+  }
+  *out = &f;
+  return ISDF_OK;
+}
+
 static cplx* g_tw[8][512];     // per device, per length: exp(-2 pi i m / n) tables (a few KB in total, never freed)
 
 static int twiddles(Handle* h, int n, const cplx** out) {
@@ -86,6 +104,34 @@ static int fft3d_reg_run(Handle* h, cplx* data, long nvec, long ldv, const int* 
   PeerArgs pr;
   for (int r = 0; r < 8; ++r) pr.peer[r] = (p2p && r < world) ? peers[r] : nullptr;
   pr.ncol = p2p ? ncol : 1; pr.row0 = row0;
+  if (group_vecs == -2 && n1 == n2 && n1 == n3) {
+    // cubic mesh, on request: both passes in one persistent launch, the intermediate stays in L2 (see
+    // fftreg_fused_kernel).  Measured on B200 (tools/fft_tune.cu, profiles/README.md): no faster than two launches,
+    // because the passes are bound on the SM side (same rate on L2-resident data), not by HBM -- kept selectable.
+    FusedSync* fs;
+    rc = fused_sync(h, &fs);
+    if (rc) return rc;
+    if (*fs->err_host) {
+      snprintf(h->err, sizeof(h->err), "isdf_fft3d_reg: a dependency wait of an earlier fused launch timed out");
+      return ISDF_ESIZE - 1;
+    }
+    const long target = 16L << 20;                       // bytes of intermediate per group
+    long gv = target / (ng * (long)sizeof(cplx));
+    if (gv < 1) gv = 1;
+    if (gv > nvec) gv = nvec;
+    long ngroups = (nvec + gv - 1) / gv;
+    if (ngroups > FUSED_MAX_GROUPS) { gv = (nvec + FUSED_MAX_GROUPS - 1) / FUSED_MAX_GROUPS; ngroups = (nvec + gv - 1) / gv; }
+    FusedArgs fa;
+    fa.pl.data = data; fa.pl.ldv = ldv; fa.pl.n1 = n1; fa.pl.nwork = nvec * n1; fa.pl.tw = twz;
+    fa.pl.pre = (const cplx*)pre_dev; fa.pl.post = nullptr; fa.pl.pr = pr;
+    fa.ln.data = data; fa.ln.ldv = ldv; fa.ln.stride = (long)n2 * n3;
+    fa.ln.tiles = (int)((fa.ln.stride + px->T - 1) / px->T); fa.ln.nwork = nvec * fa.ln.tiles; fa.ln.tw = twx;
+    fa.ln.post = post_dev; fa.ln.pr = pr;
+    fa.sync = fs->sync; fa.err = fs->err_dev; fa.nvec = nvec; fa.gv = (int)gv; fa.ngroups = (int)ngroups;
+    fa.np = (int)(gv * n1); fa.nx = (int)(gv * fa.ln.tiles);
+    ISDF_CUDA(h, cudaMemsetAsync(fs->sync, 0, sizeof(int) * (size_t)(ngroups + 1), st));
+    return pz->fused(h, fa, p2p, st);
+  }
   if (group_vecs <= 0) group_vecs = nvec;
   for (long v0 = 0; v0 < nvec; v0 += group_vecs) {
     const long nv = (nvec - v0 < group_vecs) ? (nvec - v0) : group_vecs;
@@ -108,8 +154,9 @@ static int fft3d_reg_run(Handle* h, cplx* data, long nvec, long ldv, const int* 
 }
 
 // Same contract as isdf_fft3d_batched: data [nvec][ldv >= ng] c128 in place,
-// out[v][G] = post[G] * sum_r data[v][r] * pre[r] * e^{-i G.r}.  group_vecs > 0: plane pass and x pass run back to
-// back on groups of that many vectors (L2 residency of the intermediate); <= 0: whole batch per pass.
+// out[v][G] = post[G] * sum_r data[v][r] * pre[r] * e^{-i G.r}.  group_vecs <= 0: one launch per pass over the whole
+// batch (default); group_vecs > 0: two launches per group of that many vectors; group_vecs == -2 on a cubic mesh: both
+// passes in one persistent launch with the intermediate held in L2 (dependency counters, fftreg_fused_kernel).
 extern "C" int isdf_fft3d_reg(void* hv, void* data, long nvec, long ldv, const int* mesh, const void* pre_dev,
                               const double* post_dev, long group_vecs, void* stream) {
   Handle* h = (Handle*)hv;
@@ -124,6 +171,6 @@ extern "C" int isdf_fft3d_reg_p2p(void* hv, void* const* peers, int world, long 
                                   long ldv, const int* mesh, const void* pre_dev, const double* post_dev, void* stream) {
   Handle* h = (Handle*)hv;
   ISDF_CHECK_ARG(h, peers && work && mesh, "null pointer");
-  return fft3d_reg_run(h, (cplx*)work, nvec, ldv, mesh, pre_dev, post_dev, 0, (cplx* const*)peers, world, ncol, row0,
+  return fft3d_reg_run(h, (cplx*)work, nvec, ldv, mesh, pre_dev, post_dev, -1, (cplx* const*)peers, world, ncol, row0,
                        (cudaStream_t)stream);
 }

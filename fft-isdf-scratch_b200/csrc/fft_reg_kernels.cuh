@@ -51,17 +51,46 @@ struct Gather {
   }
 };
 
-template <class AX, int THREADS, int MINB, bool P2P>
-__global__ void __launch_bounds__(THREADS, MINB) fftreg_plane_kernel(PlaneArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ cplx* peer_s[8];
-  constexpr int N = AX::N;
-  cplx* P = reinterpret_cast<cplx*>(smem_raw);
-  cplx* TW = P + AX::SLOTS;
-  for (int i = threadIdx.x; i < N; i += THREADS) TW[i] = p.tw[i];
-  if (P2P && threadIdx.x < 8) peer_s[threadIdx.x] = p.pr.peer[threadIdx.x];
-  __syncthreads();
-  for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+// global-memory access flavours: 0 default, 1 streaming (evict-first: touched once), 2 L2 only (coherent with other SMs)
+template <int KIND>
+__device__ __forceinline__ cplx ldg(const cplx* p) {
+  if (KIND == 1) return __ldcs(p);
+  if (KIND == 2) return __ldcg(p);
+  return *p;
+}
+template <int KIND>
+__device__ __forceinline__ void stg(cplx* p, cplx v) {
+  if (KIND == 1) __stcs(p, v);
+  else *p = v;
+}
+
+// x-pass store: grid index g of (vec) -> local vector or the owning rank's shard
+template <bool P2P, int STK>
+struct XStore {
+  cplx* base; const double* post; long stride; cplx* const* peer; long ncol, rowoff; long l0;
+  __device__ __forceinline__ void operator()(int k, int l, cplx v) const {
+    const long g = (long)k * stride + l0 + l;
+    if (post) { const double w = post[g]; v.x *= w; v.y *= w; }
+    if (P2P) {
+      const unsigned owner = (unsigned)g / (unsigned)ncol;
+      peer[owner][rowoff + (g - (long)owner * ncol)] = v;
+    } else {
+      stg<STK>(base + g, v);
+    }
+  }
+};
+
+// ---- one unit of work per CTA round: "ops" shared by the two-pass kernels and the fused single-launch kernel --------
+// FUSED: input loads are streaming, the x pass reads the intermediate through L2 only and streams its result out, so
+// that the intermediate written by the plane pass is what stays in L2.  Every op ends with its threads' last shared-
+// memory reads still in flight: the caller barriers before the buffer is reused.
+template <class AX_, int THREADS>
+struct PlaneTwo {
+  using AX = AX_;
+  static constexpr int WORK = AX::SLOTS;          // complex elements of shared memory besides the twiddles
+  template <bool P2P, bool FUSED>
+  static __device__ __forceinline__ void run(const PlaneArgs& p, cplx* const* peer_s, long work, cplx* P, const cplx* TW) {
+    constexpr int N = AX::N;
     const int plane = (int)(work % p.n1);
     const long vec = work / p.n1;
     const long poff = (long)plane * N * N;
@@ -72,7 +101,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fftreg_plane_kernel(PlaneArgs p
       const Gather ga(peer_s, p.pr, vec, poff);
       plane_z1<AX, THREADS>(threadIdx.x, [&](int idx) { cplx v = *ga.at(idx); if (pre) v = c_mul(v, pre[idx]); return v; }, P, TW);
     } else {
-      plane_z1<AX, THREADS>(threadIdx.x, [&](int idx) { cplx v = base[idx]; if (pre) v = c_mul(v, pre[idx]); return v; }, P, TW);
+      plane_z1<AX, THREADS>(threadIdx.x, [&](int idx) { cplx v = ldg<FUSED ? 1 : 0>(base + idx); if (pre) v = c_mul(v, pre[idx]); return v; }, P, TW);
     }
     __syncthreads();
     plane_z2<AX, THREADS>(threadIdx.x, P);
@@ -83,37 +112,16 @@ __global__ void __launch_bounds__(THREADS, MINB) fftreg_plane_kernel(PlaneArgs p
       if (post) { const double w = post[o]; v.x *= w; v.y *= w; }
       base[o] = v;
     });
-    __syncthreads();
-  }
-}
-
-// x-pass store: grid index g of (vec) -> local vector or the owning rank's shard
-template <bool P2P>
-struct XStore {
-  cplx* base; const double* post; long stride; cplx* const* peer; long ncol, rowoff; long l0;
-  __device__ __forceinline__ void operator()(int k, int l, cplx v) const {
-    const long g = (long)k * stride + l0 + l;
-    if (post) { const double w = post[g]; v.x *= w; v.y *= w; }
-    if (P2P) {
-      const unsigned owner = (unsigned)g / (unsigned)ncol;
-      peer[owner][rowoff + (g - (long)owner * ncol)] = v;
-    } else {
-      base[g] = v;
-    }
   }
 };
 
-template <class AX, int T, int THREADS, int MINB, bool P2P>
-__global__ void __launch_bounds__(THREADS, MINB) fftreg_lines_kernel(LinesArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ cplx* peer_s[8];
-  constexpr int N = AX::N;
-  cplx* S = reinterpret_cast<cplx*>(smem_raw);
-  cplx* TW = S + N * T;
-  for (int i = threadIdx.x; i < N; i += THREADS) TW[i] = p.tw[i];
-  if (P2P && threadIdx.x < 8) peer_s[threadIdx.x] = p.pr.peer[threadIdx.x];
-  __syncthreads();
-  for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+template <class AX_, int T_, int THREADS>
+struct LinesTwo {
+  using AX = AX_;
+  static constexpr int T = T_;
+  static constexpr int WORK = AX::N * T_;
+  template <bool P2P, bool FUSED>
+  static __device__ __forceinline__ void run(const LinesArgs& p, cplx* const* peer_s, long work, cplx* S, const cplx* TW) {
     const int tile = (int)(work % p.tiles);
     const long vec = work / p.tiles;
     const long l0 = (long)tile * T;
@@ -121,26 +129,23 @@ __global__ void __launch_bounds__(THREADS, MINB) fftreg_lines_kernel(LinesArgs p
     cplx* base = p.data + vec * p.ldv;
     const cplx* src = base + l0;
     const long stride = p.stride;
-    lines_s1<AX, T, THREADS>(threadIdx.x, [&](int x, int l) { return src[(long)x * stride + l]; }, lcnt, S, TW);
+    lines_s1<AX, T, THREADS>(threadIdx.x, [&](int x, int l) { return ldg<FUSED ? 2 : 0>(src + (long)x * stride + l); }, lcnt, S, TW);
     __syncthreads();
-    const XStore<P2P> st{base, p.post, stride, peer_s, p.pr.ncol, (p.pr.row0 + vec) * p.pr.ncol, l0};
+    const XStore<P2P, FUSED ? 1 : 0> st{base, p.post, stride, peer_s, p.pr.ncol, (p.pr.row0 + vec) * p.pr.ncol, l0};
     lines_s2<AX, T, THREADS>(threadIdx.x, S, lcnt, st);
-    __syncthreads();
   }
-}
+};
 
-// ---- prime lengths ---------------------------------------------------------------------------------------------
-template <class AX, int THREADS, int MINB, bool P2P>
-__global__ void __launch_bounds__(THREADS, MINB) fftreg_plane_direct_kernel(PlaneArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ cplx* peer_s[8];
-  constexpr int N = AX::N, G = AX::G, PITCH = AX::PITCH;
-  constexpr int LP = (N + 31) / 32 * 32;            // lines padded to whole warps: the group index is warp-uniform
-  cplx* A = reinterpret_cast<cplx*>(smem_raw);      // A[z][y]
-  cplx* B = A + AX::SLOTS;                          // B[kz][y]
-  if (P2P && threadIdx.x < 8) peer_s[threadIdx.x] = p.pr.peer[threadIdx.x];
-  __syncthreads();
-  for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+// prime lengths
+template <class AX_, int THREADS>
+struct PlaneDirect {
+  using AX = AX_;
+  static constexpr int WORK = 2 * AX::SLOTS;
+  template <bool P2P, bool FUSED>
+  static __device__ __forceinline__ void run(const PlaneArgs& p, cplx* const* peer_s, long work, cplx* A, const cplx*) {
+    constexpr int N = AX::N, G = AX::G, PITCH = AX::PITCH;
+    constexpr int LP = (N + 31) / 32 * 32;            // lines padded to whole warps: the group index is warp-uniform
+    cplx* B = A + AX::SLOTS;                          // A[z][y], B[kz][y]
     const int plane = (int)(work % p.n1);
     const long vec = work / p.n1;
     const long poff = (long)plane * N * N;
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fftreg_plane_direct_kernel(Plan
 #pragma unroll 4
     for (int f = threadIdx.x; f < N * N; f += THREADS) {
       const int y = f / N, z = f % N;
-      cplx v = P2P ? *ga.at(f) : base[f];
+      cplx v = P2P ? *ga.at(f) : ldg<FUSED ? 1 : 0>(base + f);
       if (pre) v = c_mul(v, pre[f]);
       A[z * PITCH + y] = v;
     }
@@ -176,33 +181,31 @@ __global__ void __launch_bounds__(THREADS, MINB) fftreg_plane_direct_kernel(Plan
                                  });
       }
     }
-    // the next round's loads overwrite A, last read before the previous barrier; B is rewritten after the next one
   }
-}
+};
 
-template <class AX, int T, int THREADS, int MINB, bool P2P>
-__global__ void __launch_bounds__(THREADS, MINB) fftreg_lines_direct_kernel(LinesArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ cplx* peer_s[8];
-  constexpr int N = AX::N, G = AX::G;
-  static_assert(T % 32 == 0, "whole warps per group");
-  cplx* S = reinterpret_cast<cplx*>(smem_raw);      // S[x][l]
-  if (P2P && threadIdx.x < 8) peer_s[threadIdx.x] = p.pr.peer[threadIdx.x];
-  for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+template <class AX_, int T_, int THREADS>
+struct LinesDirect {
+  using AX = AX_;
+  static constexpr int T = T_;
+  static constexpr int WORK = AX::N * T_;
+  static_assert(T_ % 32 == 0, "whole warps per group");
+  template <bool P2P, bool FUSED>
+  static __device__ __forceinline__ void run(const LinesArgs& p, cplx* const* peer_s, long work, cplx* S, const cplx*) {
+    constexpr int N = AX::N, G = AX::G;
     const int tile = (int)(work % p.tiles);
     const long vec = work / p.tiles;
     const long l0 = (long)tile * T;
     const int lcnt = (int)((p.stride - l0 < T) ? (p.stride - l0) : T);
     cplx* base = p.data + vec * p.ldv;
     const cplx* src = base + l0;
-    __syncthreads();
 #pragma unroll 4
     for (int f = threadIdx.x; f < N * T; f += THREADS) {
       const int x = f / T, l = f % T;
-      if (l < lcnt) S[f] = src[(long)x * p.stride + l];
+      if (l < lcnt) S[f] = ldg<FUSED ? 2 : 0>(src + (long)x * p.stride + l);
     }
     __syncthreads();
-    const XStore<P2P> st{base, p.post, p.stride, peer_s, p.pr.ncol, (p.pr.row0 + vec) * p.pr.ncol, l0};
+    const XStore<P2P, FUSED ? 1 : 0> st{base, p.post, p.stride, peer_s, p.pr.ncol, (p.pr.row0 + vec) * p.pr.ncol, l0};
     for (int i = threadIdx.x; i < G * T; i += THREADS) {
       const int g = i / T, l = i % T;
       if (l < lcnt) {
@@ -210,14 +213,104 @@ __global__ void __launch_bounds__(THREADS, MINB) fftreg_lines_direct_kernel(Line
       }
     }
   }
+};
+
+// ---- two-pass kernels: persistent CTAs, static round-robin over the units ------------------------------------
+template <class OP, class ARGS, int THREADS, int MINB, bool P2P>
+__global__ void __launch_bounds__(THREADS, MINB) fftreg_pass_kernel(ARGS p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ cplx* peer_s[8];
+  constexpr int N = OP::AX::N;
+  cplx* TW = reinterpret_cast<cplx*>(smem_raw);
+  cplx* W = TW + N;
+  for (int i = threadIdx.x; i < N; i += THREADS) TW[i] = p.tw[i];
+  if (P2P && threadIdx.x < 8) peer_s[threadIdx.x] = p.pr.peer[threadIdx.x];
+  __syncthreads();
+  for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+    OP::template run<P2P, false>(p, peer_s, work, W, TW);
+    __syncthreads();
+  }
+}
+
+// ---- fused single launch: plane pass and x pass of the whole batch in ONE persistent kernel ------------------------
+// The batch is cut into groups of gv vectors (a few tens of MB).  Units are handed out by a global ticket counter in
+// the order P(0), P(1), X(0), P(2), X(1), ...: an x unit of group g waits (acquire on done[g]) until all plane units of
+// its group have been published (release), which by ticket order are already running or finished -- no CTA ever waits
+// on work that has not been handed out, so the scheme cannot deadlock, and the intermediate of at most ~3 groups is
+// live in L2 between its write and its only read: HBM sees each element once in and once out.
+struct FusedArgs {
+  PlaneArgs pl;
+  LinesArgs ln;
+  int* sync;              // [0] ticket, [1 + g] plane units of group g published
+  int* err;               // host-mapped sticky flag: a dependency wait gave up
+  long nvec;
+  int gv, ngroups;
+  int np, nx;             // plane / x units per (full) group
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <class POP, class LOP, int THREADS, int MINB, bool P2P>
+__global__ void __launch_bounds__(THREADS, MINB) fftreg_fused_kernel(FusedArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ cplx* peer_s[8];
+  __shared__ int ticket_s;
+  constexpr int NZ = POP::AX::N, NX = LOP::AX::N;
+  cplx* TWz = reinterpret_cast<cplx*>(smem_raw);
+  cplx* TWx = TWz + NZ;
+  cplx* W = TWx + NX;
+  for (int i = threadIdx.x; i < NZ; i += THREADS) TWz[i] = p.pl.tw[i];
+  for (int i = threadIdx.x; i < NX; i += THREADS) TWx[i] = p.ln.tw[i];
+  if (P2P && threadIdx.x < 8) peer_s[threadIdx.x] = p.pl.pr.peer[threadIdx.x];
+  const long seg = (long)p.np + p.nx;
+  const long total = (long)p.ngroups * seg;
+  for (;;) {
+    __syncthreads();                                   // previous unit's shared-memory reads are done; ticket_s is free
+    if (threadIdx.x == 0) ticket_s = atomicAdd(p.sync, 1);
+    __syncthreads();
+    const long t = ticket_s;
+    if (t >= total) break;
+    // ticket order: P(0) | P(1) X(0) | P(2) X(1) | ... | X(G-1)
+    int g; long r; bool is_plane;
+    if (t < p.np) { g = 0; r = t; is_plane = true; }
+    else {
+      const long u = t - p.np;
+      const int s = (int)(u / seg) + 1;
+      r = u - (long)(s - 1) * seg;
+      if (s < p.ngroups && r < p.np) { g = s; is_plane = true; }
+      else { g = s - 1; if (s < p.ngroups) r -= p.np; is_plane = false; }
+    }
+    if (is_plane) {
+      const long vec = (long)g * p.gv + r / p.pl.n1;
+      if (vec < p.nvec) POP::template run<P2P, true>(p.pl, peer_s, vec * p.pl.n1 + r % p.pl.n1, W, TWz);
+      __threadfence();                                 // this thread's stores are visible device-wide ...
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(p.sync + 1 + g, 1);   // ... before the unit is published
+    } else {
+      if (threadIdx.x == 0) {
+        int spins = 0;
+        while (ld_acquire(p.sync + 1 + g) < p.np) {
+          __nanosleep(128);
+          if (++spins > (1 << 24)) { *((volatile int*)p.err) = 1; break; }
+        }
+      }
+      __syncthreads();
+      const long vec = (long)g * p.gv + r / p.ln.tiles;
+      if (vec < p.nvec) LOP::template run<P2P, true>(p.ln, peer_s, vec * p.ln.tiles + r % p.ln.tiles, W, TWx);
+    }
+  }
 }
 
 // ---- host side: plan table ---------------------------------------------------------------------------------
 struct RegPlan {
   int n;
-  size_t plane_smem, lines_smem;
   int (*plane)(Handle*, const PlaneArgs&, bool p2p, cudaStream_t);
   int (*lines)(Handle*, const LinesArgs&, bool p2p, cudaStream_t);
+  int (*fused)(Handle*, const FusedArgs&, bool p2p, cudaStream_t);     // cubic meshes: n1 == n2 == n3 == n
   int T;
 };
 
@@ -233,45 +326,38 @@ static inline int resident_grid(Handle* h, K kernel, int threads, size_t smem, l
 }
 
 template <class K, class A>
-static int launch_resident(Handle* h, K kernel, int threads, size_t smem, const A& a, cudaStream_t st) {
+static int launch_resident(Handle* h, K kernel, int threads, size_t smem, const A& a, long nwork, cudaStream_t st) {
   long grid;
-  int rc = resident_grid(h, kernel, threads, smem, a.nwork, &grid);
+  int rc = resident_grid(h, kernel, threads, smem, nwork, &grid);
   if (rc) return rc;
   kernel<<<(unsigned)grid, threads, smem, st>>>(a);
   ISDF_LAUNCH_CHECK(h);
   return ISDF_OK;
 }
-template <class AX, int THREADS, int MINB>
-static int launch_plane(Handle* h, const PlaneArgs& a, bool p2p, cudaStream_t st) {
-  const size_t smem = (size_t)(AX::SLOTS + AX::N) * sizeof(cplx);
-  return p2p ? launch_resident(h, fftreg_plane_kernel<AX, THREADS, MINB, true>, THREADS, smem, a, st)
-             : launch_resident(h, fftreg_plane_kernel<AX, THREADS, MINB, false>, THREADS, smem, a, st);
+template <class OP, class ARGS, int THREADS, int MINB>
+static int launch_pass(Handle* h, const ARGS& a, bool p2p, cudaStream_t st) {
+  const size_t smem = (size_t)(OP::WORK + OP::AX::N) * sizeof(cplx);
+  return p2p ? launch_resident(h, fftreg_pass_kernel<OP, ARGS, THREADS, MINB, true>, THREADS, smem, a, a.nwork, st)
+             : launch_resident(h, fftreg_pass_kernel<OP, ARGS, THREADS, MINB, false>, THREADS, smem, a, a.nwork, st);
 }
-template <class AX, int T, int THREADS, int MINB>
-static int launch_lines(Handle* h, const LinesArgs& a, bool p2p, cudaStream_t st) {
-  const size_t smem = (size_t)(AX::N * T + AX::N) * sizeof(cplx);
-  return p2p ? launch_resident(h, fftreg_lines_kernel<AX, T, THREADS, MINB, true>, THREADS, smem, a, st)
-             : launch_resident(h, fftreg_lines_kernel<AX, T, THREADS, MINB, false>, THREADS, smem, a, st);
-}
-template <class AX, int THREADS, int MINB>
-static int launch_plane_direct(Handle* h, const PlaneArgs& a, bool p2p, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * AX::SLOTS) * sizeof(cplx);
-  return p2p ? launch_resident(h, fftreg_plane_direct_kernel<AX, THREADS, MINB, true>, THREADS, smem, a, st)
-             : launch_resident(h, fftreg_plane_direct_kernel<AX, THREADS, MINB, false>, THREADS, smem, a, st);
-}
-template <class AX, int T, int THREADS, int MINB>
-static int launch_lines_direct(Handle* h, const LinesArgs& a, bool p2p, cudaStream_t st) {
-  const size_t smem = (size_t)(AX::N * T) * sizeof(cplx);
-  return p2p ? launch_resident(h, fftreg_lines_direct_kernel<AX, T, THREADS, MINB, true>, THREADS, smem, a, st)
-             : launch_resident(h, fftreg_lines_direct_kernel<AX, T, THREADS, MINB, false>, THREADS, smem, a, st);
+template <class POP, class LOP, int THREADS, int MINB>
+static int launch_fused(Handle* h, const FusedArgs& a, bool p2p, cudaStream_t st) {
+  constexpr int WORK = POP::WORK > LOP::WORK ? POP::WORK : LOP::WORK;
+  const size_t smem = (size_t)(WORK + POP::AX::N + LOP::AX::N) * sizeof(cplx);
+  const long total = (long)a.ngroups * ((long)a.np + a.nx);
+  return p2p ? launch_resident(h, fftreg_fused_kernel<POP, LOP, THREADS, MINB, true>, THREADS, smem, a, total, st)
+             : launch_resident(h, fftreg_fused_kernel<POP, LOP, THREADS, MINB, false>, THREADS, smem, a, total, st);
 }
 
 // N = R1 x R2 | plane kernel: threads, min CTAs per SM | x pass: lines per tile, threads, min CTAs per SM
-#define ISDF_FFT_TWO(N, R1, R2, PT, PB, T, LT, LB)                                                   \
-  {N, 0, 0, launch_plane<TwoFactor<N, R1, R2>, PT, PB>, launch_lines<TwoFactor<N, R1, R2>, T, LT, LB>, T}
-#define ISDF_FFT_DIRECT(N, G, PT, PB, T, LT, LB)                                                     \
-  {N, 0, 0, launch_plane_direct<Direct<N, G>, PT, PB>, launch_lines_direct<Direct<N, G>, T, LT, LB>, T}
-
+#define ISDF_FFT_TWO(N, R1, R2, PT, PB, T, LT, LB)                                                        \
+  {N, launch_pass<PlaneTwo<TwoFactor<N, R1, R2>, PT>, PlaneArgs, PT, PB>,                                 \
+   launch_pass<LinesTwo<TwoFactor<N, R1, R2>, T, LT>, LinesArgs, LT, LB>,                                 \
+   launch_fused<PlaneTwo<TwoFactor<N, R1, R2>, PT>, LinesTwo<TwoFactor<N, R1, R2>, T, PT>, PT, PB>, T}
+#define ISDF_FFT_DIRECT(N, G, PT, PB, T, LT, LB)                                                          \
+  {N, launch_pass<PlaneDirect<Direct<N, G>, PT>, PlaneArgs, PT, PB>,                                      \
+   launch_pass<LinesDirect<Direct<N, G>, T, LT>, LinesArgs, LT, LB>,                                      \
+   launch_fused<PlaneDirect<Direct<N, G>, PT>, LinesDirect<Direct<N, G>, T, PT>, PT, PB>, T}
 
 struct RegPlanSlice { const RegPlan* plans; int count; };
 }  // namespace fftreg

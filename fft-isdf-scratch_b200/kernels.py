@@ -488,7 +488,11 @@ class IsdfOps:
             else:
                 smooth = all(self._max_prime_factor(int(x)) <= 13 for x in mesh)
                 mode = "stockham" if ((smooth and max(int(x) for x in mesh) > 32) or not fits) else "dmma"
-        if mode == "reg":
+        if mode in ("reg", "reg-fused"):
+            # "reg-fused": cubic meshes, both passes in one persistent launch (measured no faster; kept selectable)
+            if mode == "reg-fused":
+                assert int(mesh[0]) == int(mesh[1]) == int(mesh[2])
+                group_vecs = -2
             self.handle.check(self.lib.isdf_fft3d_reg(self.h, _ptr(data), nvec, ldv, m, _ptr(pre), _ptr(post),
                                                       int(group_vecs), _stream()), "isdf_fft3d_reg")
             ngroups = 1 if group_vecs <= 0 else -(-nvec // int(group_vecs))

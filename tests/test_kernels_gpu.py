@@ -259,6 +259,13 @@ def test_fft3d_register_kernels(ops, mesh):
     ops.fft3d(d, mesh, nvec=nvec, ldv=ldv)                 # auto routing picks the same kernels; no phase / weight
     ref = np.fft.fftn(x[:, :ng].reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng)
     assert relerr(d.cpu().numpy()[:, :ng], ref) < 1e-13
+    if mesh[0] == mesh[1] == mesh[2]:                      # single persistent launch with dependency counters
+        nvec = 70 if ng < 40000 else 9                     # several groups of vectors
+        x = crand(rng, nvec, ng)
+        d = dev(x.copy())
+        ops.fft3d(d, mesh, pre=dev(pre), post=dev(post), mode="reg-fused")
+        ref = np.fft.fftn((x * pre).reshape(nvec, *mesh), axes=(1, 2, 3)).reshape(nvec, ng) * post
+        assert relerr(d.cpu().numpy(), ref) < 1e-13
 
 
 def test_fft3d_register_kernels_every_length(ops):

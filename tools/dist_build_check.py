@@ -52,6 +52,33 @@ def main():
             e2 = float(np.abs(dn._wq - g["wq"]).max() / np.abs(g["wq"]).max())
             assert e2 < 1e-10, e2
     assert worst < 1e-11, worst
+    # kernel level: the NVLink gather/scatter variants of both transform families == the local transform of the
+    # gathered vectors (register-resident FFT: two-factor 33^3, prime 37 x two-factor 15^2; tensor-core DFT 9^3)
+    from fft_isdf_scratch_b200 import kernels, sharding
+    ops = kernels.IsdfOps(local)
+    for mesh, mode in [([33, 33, 33], "reg"), ([37, 15, 15], "reg"), ([9, 9, 9], "dmma"), ([33, 33, 33], "dmma")]:
+        ng = int(np.prod(mesh))
+        lo, hi, ncol = sharding.col_shard(ng, world, rank)
+        rows = 6 * world
+        gen = torch.Generator(device="cpu").manual_seed(7)
+        full = torch.randn(rows, ncol * world, dtype=torch.complex128, generator=gen)
+        full[:, ng:] = 0
+        pre = torch.randn(ng, dtype=torch.complex128, generator=gen).cuda()
+        post = torch.rand(ng, dtype=torch.float64, generator=gen).cuda()
+        buf = sharding.PeerBuffer((rows, ncol), torch.device("cuda", local), dist.group.WORLD)
+        buf.tensor.copy_(full[:, rank * ncol:(rank + 1) * ncol])
+        v_lo, v_cnt = sharding.vector_shard(rows, world, rank)
+        work = torch.empty((v_cnt, ng), dtype=torch.complex128, device="cuda")
+        buf.barrier()
+        ops.dft3d_p2p(buf.ptrs, ncol, v_lo, work, v_cnt, mesh, pre=pre, post=post, mode=mode)
+        buf.barrier()
+        ref = full[:, :ng].cuda().clone()
+        ops.fft3d(ref, mesh, pre=pre, post=post)
+        got = buf.tensor[:, : min(hi, ng) - lo] if hi > lo else buf.tensor[:, :0]
+        e3 = float((got - ref[:, lo:min(hi, ng)]).abs().max() / ref.abs().max()) if hi > lo else 0.0
+        print(f"rank {rank}/{world} p2p {mode} {mesh}: {e3:.2e}", flush=True)
+        assert e3 < 1e-13, e3
+        del buf
     dist.barrier()
     if rank == 0:
         print("DIST_OK", worst, flush=True)

@@ -260,6 +260,25 @@ extern "C" int isdf_gemm_hn(void* hv, const void* a, long lda, long strideA, con
   return ISDF_OK;
 }
 
+// C = A^H B for a product KNOWN to be Hermitian (W = E^H (W~ E)): only the tiles on and below the diagonal are
+// computed, the upper triangle is the mirrored conjugate and the diagonal gets an exact zero imaginary part
+// (the HERK epilogue), i.e. gemm_hn + hermitize at ~half the tensor work.
+extern "C" int isdf_gemm_hn_herm(void* hv, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                                 void* c, long ldc, long strideC, int n, int k, int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, a && b && c, "null pointer");
+  ISDF_CHECK_ARG(h, n >= 0 && k >= 0 && batch >= 0 && batch <= 65535, "shape");
+  GemmParams p;
+  p.A = (const cplx*)a; p.lda = lda; p.strideA = strideA;
+  p.B = (const cplx*)b; p.ldb = ldb; p.strideB = strideB;
+  p.C = (cplx*)c; p.ldc = ldc; p.strideC = strideC;
+  p.M = n; p.N = n; p.K = k;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = 1.0;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
+  ISDF_CUDA(h, (launch_gemm<128, 64, true, true, MODE_CONJA, false, EPI_HERK>(p, batch, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
 extern "C" int isdf_rowdot_conj_sum(void* hv, const void* y, const void* x, int nz, int nrows, int ncols, double scale,
                                     void* out, void* stream) {
   Handle* h = (Handle*)hv;

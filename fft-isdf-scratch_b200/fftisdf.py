@@ -442,7 +442,7 @@ def build(df_obj):
         with ops.timed("expand_w"):                                        # W_q = E W~ E^H for this rank's slots
             if mine:
                 wt_l = wt[mine].contiguous() if world > 1 else wt
-                w_l = ops.hermitize(ops.gemm_hn(eh_l, ops.gemm_nn(wt_l, eh_l)))
+                w_l = ops.gemm_hn_herm(eh_l, ops.gemm_nn(wt_l, eh_l))      # Hermitian by construction: lower tiles
                 del wt_l
             else:
                 w_l = torch.zeros((0, nip, nip), dtype=torch.complex128, device=dev)

@@ -179,6 +179,18 @@ class IsdfOps:
         self.launches += 1
         return out
 
+    def gemm_hn_herm(self, a, b):
+        """out[z] = a[z]^H @ b[z] for a product known to be Hermitian: lower tiles + mirrored conjugate (exactly
+        Hermitian output, half the tensor work of gemm_hn + hermitize); a, b [batch,k,n]."""
+        _chk(a, c128), _chk(b, c128)
+        batch, k, n = a.shape
+        assert b.shape == a.shape
+        out = torch.empty((batch, n, n), dtype=c128, device=self.device)
+        self.handle.check(self.lib.isdf_gemm_hn_herm(self.h, _ptr(a), n, k * n, _ptr(b), n, k * n, _ptr(out), n, n * n,
+                                                     n, k, batch, _stream()), "isdf_gemm_hn_herm")
+        self.launches += 1
+        return out
+
     def rowdot_conj_sum(self, y, x, scale):
         _chk(y, c128), _chk(x, c128)
         nz, nrows, ncols = x.shape

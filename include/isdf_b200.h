@@ -173,6 +173,10 @@ int isdf_gelsy_q1_finish(void* handle, void* vm, const double* dinv, const int* 
 int isdf_gelsy_q1h_finish(void* handle, void* t1, const double* dinv, const int* rank, int n, int rP, int batch,
                           void* stream);
 int isdf_hermitize(void* handle, void* w, int n, int batch, void* stream);
+/* c[z] [n,n] = a[z]^H b[z] for a product known to be Hermitian (W_q = E (W~ E^H), fftisdf.py:121 in the row space of
+ * zgelsy): lower tiles only, mirrored conjugate above, exact real diagonal.  a, b: [k][n] per batch. */
+int isdf_gemm_hn_herm(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
+                      void* c, long ldc, long strideC, int n, int k, int batch, void* stream);
 int isdf_gemm_tn(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB, void* c,
                  long ldc, long strideC, int m, int n, int k, int batch, void* stream);
 

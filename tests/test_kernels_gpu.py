@@ -284,6 +284,21 @@ def test_fft3d_register_kernels_every_length(ops):
     assert not ops.fft3d_reg_supported([8, 64, 32]) and not ops.fft3d_reg_supported([4, 127, 127])
 
 
+def test_gemm_hn_herm(ops):
+    """a^H (H a) with Hermitian H: the lower-tile product equals the full product, exactly Hermitian, real diagonal."""
+    rng = np.random.default_rng(41)
+    for k, n in [(70, 157), (130, 64), (33, 200)]:
+        a = crand(rng, 2, k, n)
+        hm = crand(rng, 2, k, k)
+        hm = hm + hm.conj().transpose(0, 2, 1)
+        b = hm @ a
+        out = ops.gemm_hn_herm(dev(a), dev(b)).cpu().numpy()
+        ref = a.conj().transpose(0, 2, 1) @ b
+        assert relerr(out, ref) < 1e-13
+        assert np.array_equal(out, out.conj().transpose(0, 2, 1))
+        assert np.all(out[:, np.arange(n), np.arange(n)].imag == 0.0)
+
+
 def test_gather_and_conj(ops):
     rng = np.random.default_rng(12)
     src = crand(rng, 2, 11, 301)

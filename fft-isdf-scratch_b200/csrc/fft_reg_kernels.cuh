@@ -9,7 +9,10 @@ namespace fftreg {
 // Multi-GPU (P2P = true): the grid columns of every vector are sharded over the ranks, peer[r] = rank r's shard
 // [rows][ncol] in NVLink peer-mapped memory (rank r owns grid points [r ncol, (r+1) ncol)).  The plane kernel GATHERS
 // its planes from the owning ranks (P2P loads) into the local work buffer `data`, the x pass SCATTERS the weighted
-// result back into the shards (P2P stores): both all-to-all exchanges are fused into the transform.
+// result back into the shards (P2P stores): both all-to-all exchanges are fused into the transform.  The gather uses
+// plain loads into the butterfly registers; a cp.async pipeline that lands the NEXT plane in a second shared-memory
+// buffer was measured slower (NiO 33^3 on 2 GPUs: 87 vs 52 ms per build) because it halves the CTAs per SM, and the
+// NVLink request rate follows the number of resident CTAs.
 struct PeerArgs {
   cplx* peer[8];
   long ncol, row0;
@@ -257,51 +260,6 @@ __global__ void __launch_bounds__(THREADS, MINB) fftreg_pass_kernel(ARGS p) {
   }
 }
 
-// ---- multi-GPU plane pass with the NVLink gather pipelined: the NEXT plane is fetched from the owning ranks' shards
-// with cp.async into a raw landing buffer while the current one is transformed, so the ~2-3k-cycle peer latency hides
-// behind three of the four phases (used when two such CTAs still fit an SM; otherwise the direct-load variant above).
-template <class AX, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) fftreg_plane_gather_kernel(PlaneArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ cplx* peer_s[8];
-  constexpr int N = AX::N;
-  cplx* TW = reinterpret_cast<cplx*>(smem_raw);
-  cplx* P = TW + N;
-  cplx* RAW = P + AX::SLOTS;                      // [y][z] as in global memory
-  for (int i = threadIdx.x; i < N; i += THREADS) TW[i] = p.tw[i];
-  if (threadIdx.x < 8) peer_s[threadIdx.x] = p.pr.peer[threadIdx.x];
-  __syncthreads();
-  auto prefetch = [&](long work) {
-    const int plane = (int)(work % p.n1);
-    const long vec = work / p.n1;
-    const Gather ga(peer_s, p.pr, vec, (long)plane * N * N);
-    for (int f = threadIdx.x; f < N * N; f += THREADS) cp_async16(RAW + f, ga.at(f), true);
-    cp_async_commit();
-  };
-  if ((long)blockIdx.x < p.nwork) prefetch(blockIdx.x);
-  for (long work = blockIdx.x; work < p.nwork; work += gridDim.x) {
-    const int plane = (int)(work % p.n1);
-    const long vec = work / p.n1;
-    const long poff = (long)plane * N * N;
-    cplx* base = p.data + vec * p.ldv + poff;
-    const cplx* pre = p.pre ? p.pre + poff : nullptr;
-    const double* post = p.post ? p.post + poff : nullptr;
-    cp_async_wait<0>();
-    __syncthreads();                               // the plane has landed; the previous round's reads of P are done
-    plane_z1<AX, THREADS>(threadIdx.x, [&](int idx) { cplx v = RAW[idx]; if (pre) v = c_mul(v, pre[idx]); return v; }, P, TW);
-    __syncthreads();
-    if (work + gridDim.x < p.nwork) prefetch(work + gridDim.x);
-    plane_z2<AX, THREADS>(threadIdx.x, P);
-    __syncthreads();
-    plane_y1<AX, THREADS>(threadIdx.x, P, TW);
-    __syncthreads();
-    plane_y2<AX, THREADS>(threadIdx.x, P, [&](int o, cplx v) {
-      if (post) { const double w = post[o]; v.x *= w; v.y *= w; }
-      base[o] = v;
-    });
-  }
-}
-
 // ---- fused single launch: plane pass and x pass of the whole batch in ONE persistent kernel ------------------------
 // The batch is cut into groups of gv vectors (a few tens of MB).  Units are handed out by a global ticket counter in
 // the order P(0), P(1), X(0), P(2), X(1), ...: an x unit of group g waits (acquire on done[g]) until all plane units of
@@ -410,13 +368,6 @@ static int launch_pass(Handle* h, const ARGS& a, bool p2p, cudaStream_t st) {
   return p2p ? launch_resident(h, fftreg_pass_kernel<OP, ARGS, THREADS, MINB, true>, THREADS, smem, a, a.nwork, st)
              : launch_resident(h, fftreg_pass_kernel<OP, ARGS, THREADS, MINB, false>, THREADS, smem, a, a.nwork, st);
 }
-template <class AX, int THREADS, int MINB>
-static int launch_plane_two(Handle* h, const PlaneArgs& a, bool p2p, cudaStream_t st) {
-  const size_t smem_g = (size_t)(AX::SLOTS + AX::N + AX::N * AX::N) * sizeof(cplx);
-  if (p2p && 2 * (smem_g + 1024) <= (size_t)h->max_smem_optin)
-    return launch_resident(h, fftreg_plane_gather_kernel<AX, THREADS, MINB>, THREADS, smem_g, a, a.nwork, st);
-  return launch_pass<PlaneTwo<AX, THREADS>, PlaneArgs, THREADS, MINB>(h, a, p2p, st);
-}
 template <class POP, class LOP, int THREADS, int MINB>
 static int launch_fused(Handle* h, const FusedArgs& a, bool p2p, cudaStream_t st) {
   constexpr int WORK = POP::WORK > LOP::WORK ? POP::WORK : LOP::WORK;
@@ -428,7 +379,7 @@ static int launch_fused(Handle* h, const FusedArgs& a, bool p2p, cudaStream_t st
 
 // N = R1 x R2 | plane kernel: threads, min CTAs per SM | x pass: lines per tile, threads, min CTAs per SM
 #define ISDF_FFT_TWO(N, R1, R2, PT, PB, T, LT, LB)                                                        \
-  {N, launch_plane_two<TwoFactor<N, R1, R2>, PT, PB>,                                                    \
+  {N, launch_pass<PlaneTwo<TwoFactor<N, R1, R2>, PT>, PlaneArgs, PT, PB>,                                 \
    launch_pass<LinesTwo<TwoFactor<N, R1, R2>, T, LT>, LinesArgs, LT, LB>,                                 \
    launch_fused<PlaneTwo<TwoFactor<N, R1, R2>, PT>, LinesTwo<TwoFactor<N, R1, R2>, T, PT>, PT, PB>, T}
 #define ISDF_FFT_DIRECT(N, G, PT, PB, T, LT, LB)                                                          \

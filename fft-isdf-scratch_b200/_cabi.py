@@ -59,6 +59,8 @@ SIGNATURES = {
     "isdf_gelsy_q1_finish": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "isdf_gelsy_q1h_finish": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "isdf_hermitize": [c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "isdf_herk_to_peers": [c_void_p, c_void_p, c_long, c_long, c_int, c_int, c_double, c_void_p, c_long, c_int, c_void_p],
+    "isdf_sum_slabs_herm": [c_void_p, c_void_p, c_int, c_int, c_long, c_long, c_void_p, c_long, c_long, c_int, c_void_p],
     "isdf_gemm_hn_herm": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_long, c_long,
                           c_int, c_int, c_int, c_void_p],
     "isdf_gemm_tn": [c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_long, c_long,

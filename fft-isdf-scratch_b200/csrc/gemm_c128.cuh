@@ -42,6 +42,10 @@ struct GemmParams {
   // N-tile, so that a B column panel fetched from DRAM is shared by group_m resident CTAs instead of being re-read for
   // every M-tile (ncu on the NiO fit GEMM: 1.23 TB of DRAM reads per launch for 32 GB of operands without it)
   int group_m = 0;
+  // EPI_HERK across GPUs: per-batch destination (e.g. a slab in the OWNING rank's NVLink peer-mapped memory), written
+  // with plain stores as the tiles finish, lower triangle only (the owner mirrors when it sums the slabs)
+  cplx* const* Cbatch = nullptr;
+  int lower_only = 0;
 };
 
 #ifndef ISDF_GEMM_BK
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN, REAL_ONLY), gemm_min_bloc
   }
   cp_async_wait<0>();
 
-  cplx* Cb = p.C + (long)bz * p.strideC + (long)ksp * p.strideSplit;
+  cplx* Cb = (EPI == EPI_HERK && p.Cbatch != nullptr) ? p.Cbatch[bz] : p.C + (long)bz * p.strideC + (long)ksp * p.strideSplit;
   const int* perm = (EPI == EPI_HERK && p.perm != nullptr) ? p.perm + (long)bz * p.stridePerm : nullptr;
   const double alpha = p.alpha;
 #pragma unroll
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(gemm_threads(BM, BN, REAL_ONLY), gemm_min_bloc
             const int pr = perm ? perm[r] : r, pc = perm ? perm[c] : c;
             // the diagonal of B B^H is real: store an exact zero imaginary part
             Cb[(long)pr * p.ldc + pc] = make_double2(alpha * vr, (r == c) ? 0.0 : alpha * vi);
-            if (r > c) Cb[(long)pc * p.ldc + pr] = make_double2(alpha * vr, -alpha * vi);
+            if (r > c && !p.lower_only) Cb[(long)pc * p.ldc + pr] = make_double2(alpha * vr, -alpha * vi);
           }
         } else {  // EPI_SQ_SYM: out = alpha * re^2 (real, stored as complex with zero imaginary part)
           if (r >= c) {

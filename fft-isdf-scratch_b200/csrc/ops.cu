@@ -225,6 +225,56 @@ extern "C" int isdf_herk_scatter(void* hv, const void* b, long ldb, long strideB
   return ISDF_OK;
 }
 
+// W~ partial products across GPUs, reduce-scatter fused into the HERK: batch z is stored (lower triangle, plain
+// stores as the tiles finish, i.e. overlapped with the tensor work) into dst[z], which the host points at this rank's
+// slab inside the OWNING rank's NVLink peer-mapped buffer.  isdf_sum_slabs_herm then sums the slabs in rank order.
+extern "C" int isdf_herk_to_peers(void* hv, const void* b, long ldb, long strideB, int n, int k, double alpha,
+                                  void* const* dst_dev, long ldw, int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, b && dst_dev, "null pointer");
+  ISDF_CHECK_ARG(h, n >= 0 && k >= 0 && batch >= 0 && batch <= 65535 && ldw >= n, "shape");
+  if (n == 0 || batch == 0) return ISDF_OK;
+  GemmParams p;
+  p.A = (const cplx*)b; p.lda = ldb; p.strideA = strideB;
+  p.B = (const cplx*)b; p.ldb = ldb; p.strideB = strideB;
+  p.C = nullptr; p.ldc = ldw; p.strideC = 0;
+  p.M = n; p.N = n; p.K = k;
+  p.nseg = 1; p.segA = 0; p.segB = 0; p.alpha = alpha;
+  p.perm = nullptr; p.stridePerm = 0; p.active = nullptr; p.ksplit = 1; p.kchunk = 0; p.strideSplit = 0;
+  p.Cbatch = (cplx* const*)dst_dev; p.lower_only = 1;
+  ISDF_CUDA(h, (launch_gemm<128, 64, false, false, MODE_CONJB, false, EPI_HERK>(p, batch, (cudaStream_t)stream)));
+  return ISDF_OK;
+}
+
+// out[z][r][c] = sum_{w < world} slabs[z][w][r][c] for r >= c (fixed order: deterministic), mirrored conjugate above,
+// exact real diagonal.  slabs [batch][world][n][ld] (only the leading n x n lower triangles are read), out [batch][n][ldo].
+__global__ void sum_slabs_herm_kernel(const cplx* __restrict__ slabs, int world, int n, long ld, long slab_stride,
+                                      cplx* __restrict__ out, long ldo, long strideO) {
+  const int z = blockIdx.z;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || c > r) return;
+  const cplx* s = slabs + (long)z * world * slab_stride + (long)r * ld + c;
+  double re = 0.0, im = 0.0;
+  for (int w = 0; w < world; ++w) { const cplx v = s[(long)w * slab_stride]; re += v.x; im += v.y; }
+  cplx* o = out + (long)z * strideO;
+  o[(long)r * ldo + c] = make_double2(re, (r == c) ? 0.0 : im);
+  if (r > c) o[(long)c * ldo + r] = make_double2(re, -im);
+}
+
+extern "C" int isdf_sum_slabs_herm(void* hv, const void* slabs, int world, int n, long ld, long slab_stride, void* out,
+                                   long ldo, long strideO, int batch, void* stream) {
+  Handle* h = (Handle*)hv;
+  ISDF_CHECK_ARG(h, slabs && out, "null pointer");
+  ISDF_CHECK_ARG(h, world >= 1 && n >= 0 && ld >= n && ldo >= n && batch >= 0 && batch <= 65535, "shape");
+  if (n == 0 || batch == 0) return ISDF_OK;
+  dim3 block(32, 8), grid((n + 31) / 32, (n + 7) / 8, batch);
+  sum_slabs_herm_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const cplx*)slabs, world, n, ld, slab_stride,
+                                                                 (cplx*)out, ldo, strideO);
+  ISDF_LAUNCH_CHECK(h);
+  return ISDF_OK;
+}
+
 // c[z] = a[z] * b[z]  with a [m][k] row-major, b [k][n] row-major (plain complex GEMM, NN)
 extern "C" int isdf_gemm_nn(void* hv, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,
                             void* c, long ldc, long strideC, int m, int n, int k, int batch, void* stream) {

@@ -435,19 +435,42 @@ def build(df_obj):
         theta = sharding.to_column_layout(vecs, comm)            # [nq][nipP][ncol]
         del vecs
     if fit == "gelsy":
-        wt = torch.zeros((nq, nipP, nipP), dtype=torch.complex128, device=dev)
-        with ops.timed("herk"):
-            ops.herk_strided(theta, ncol, nipP * ncol, rmax, ncol, 1.0, None, 0, wt, nipP, nipP * nipP, nq)  # :121
-        sharding.allreduce_sum_(wt, comm)
+        if world > 1 and getattr(df_obj, "exchange", "p2p") == "p2p":
+            # reduce-scatter of the partial W~ fused into the HERK: every q-slot is stored (lower triangle, as its tiles
+            # finish) straight into this rank's slab inside the slot OWNER's NVLink peer-mapped buffer; after one
+            # cross-rank barrier the owner sums the `world` slabs in rank order (deterministic, exactly Hermitian).
+            n_own = -(-nq // world)
+            cache = df_obj.__dict__.setdefault("_slab_cache", {})
+            key = (n_own, world, nipP)
+            if key not in cache:
+                cache.clear()
+                cache[key] = sharding.PeerBuffer((n_own, world, nipP, nipP), dev, comm)
+            slabs = cache[key]
+            dst = [slabs.ptrs[s % world] + 16 * ((s // world) * world + rank) * nipP * nipP for s in range(nq)]
+            assert mine == list(range(rank, nq, world))          # slot s lives on rank s % world at index s // world
+            dst_d = torch.tensor(dst, dtype=torch.int64, device=dev)
+            slabs.barrier()                                      # the owners are done with the previous build's slabs
+            with ops.timed("herk"):
+                ops.herk_to_peers(theta, ncol, nipP * ncol, rmax, ncol, 1.0, dst_d, nipP, nq)               # :121
+            slabs.barrier()                                      # every rank's stores have landed
+            wt_l = torch.zeros((len(mine), nipP, nipP), dtype=torch.complex128, device=dev)
+            if mine:
+                ops.sum_slabs_herm(slabs.tensor[: len(mine)], world, rmax, wt_l)
+        else:
+            wt = torch.zeros((nq, nipP, nipP), dtype=torch.complex128, device=dev)
+            with ops.timed("herk"):
+                ops.herk_strided(theta, ncol, nipP * ncol, rmax, ncol, 1.0, None, 0, wt, nipP, nipP * nipP, nq)  # :121
+            sharding.allreduce_sum_(wt, comm)
+            wt_l = (wt[mine].contiguous() if world > 1 else wt) if mine else None
+            del wt
         with ops.timed("expand_w"):                                        # W_q = E W~ E^H for this rank's slots
             if mine:
-                wt_l = wt[mine].contiguous() if world > 1 else wt
                 w_l = ops.gemm_hn_herm(eh_l, ops.gemm_nn(wt_l, eh_l))      # Hermitian by construction: lower tiles
-                del wt_l
             else:
                 w_l = torch.zeros((0, nip, nip), dtype=torch.complex128, device=dev)
+        del wt_l
         wslot = sharding.allgather_slots(w_l, nq, comm)
-        del wt, eh_l, w_l
+        del eh_l, w_l
     else:
         wslot = torch.zeros((nq, nip, nip), dtype=torch.complex128, device=dev)
         nrow = min(nip, rmax)

@@ -553,6 +553,24 @@ class IsdfOps:
                           "isdf_herk_scatter")
         self.launches += 1
 
+    def herk_to_peers(self, b, ldb, strideB, n, k, alpha, dst_ptrs, ldw, batch):
+        """W~ partial products with the reduce-scatter fused in: batch z goes (lower triangle, plain NVLink stores as
+        the tiles finish) to dst_ptrs[z], a DEVICE int64 tensor of peer-mapped addresses (see the C header)."""
+        assert dst_ptrs.dtype == torch.int64 and dst_ptrs.is_cuda and dst_ptrs.numel() == batch
+        self.handle.check(self.lib.isdf_herk_to_peers(self.h, _ptr(b), ldb, strideB, n, k, float(alpha), _ptr(dst_ptrs),
+                                                      ldw, batch, _stream()), "isdf_herk_to_peers")
+        self.launches += 1
+
+    def sum_slabs_herm(self, slabs, world, n, out):
+        """out[z] = sum of the `world` lower-triangular slabs slabs[z, w] in rank order, mirrored (exactly Hermitian)."""
+        _chk(slabs, c128), _chk(out, c128)
+        batch, w, ldn, ld = slabs.shape
+        assert w == world and out.shape[0] == batch
+        self.handle.check(self.lib.isdf_sum_slabs_herm(self.h, _ptr(slabs), world, n, ld, ldn * ld, _ptr(out),
+                                                       out.shape[2], out.shape[1] * out.shape[2], batch, _stream()),
+                          "isdf_sum_slabs_herm")
+        self.launches += 1
+
     # ---- device-side per-q tables (fftisdf.py:99, :114-115) -----------------------------------
     def coulomb_weights(self, b, kscaled, mesh, vol, out):
         bb = (C.c_double * 9)(*[float(x) for x in np.asarray(b).reshape(9)])

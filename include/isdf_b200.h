@@ -173,6 +173,15 @@ int isdf_gelsy_q1_finish(void* handle, void* vm, const double* dinv, const int* 
 int isdf_gelsy_q1h_finish(void* handle, void* t1, const double* dinv, const int* rank, int n, int rP, int batch,
                           void* stream);
 int isdf_hermitize(void* handle, void* w, int n, int batch, void* stream);
+/* Multi-GPU form of the W~ = B~ B~^H contraction (fftisdf.py:121) with the reduce-scatter over the ranks fused into
+ * the product: batch z (a q-slot) is stored -- lower triangle, as its tiles finish -- into dst[z] (DEVICE array of
+ * `batch` pointers), which the host points at this rank's slab [n][ldw] inside the slot OWNER's NVLink peer-mapped
+ * buffer.  After a cross-rank barrier the owner calls isdf_sum_slabs_herm: out[z] = sum over the `world` slabs in
+ * rank order (deterministic), mirrored, exact real diagonal.  slabs [batch][world][slab_stride], out [batch][n][ldo]. */
+int isdf_herk_to_peers(void* handle, const void* b, long ldb, long strideB, int n, int k, double alpha,
+                       void* const* dst_dev, long ldw, int batch, void* stream);
+int isdf_sum_slabs_herm(void* handle, const void* slabs, int world, int n, long ld, long slab_stride, void* out,
+                        long ldo, long strideO, int batch, void* stream);
 /* c[z] [n,n] = a[z]^H b[z] for a product known to be Hermitian (W_q = E (W~ E^H), fftisdf.py:121 in the row space of
  * zgelsy): lower tiles only, mirrored conjugate above, exact real diagonal.  a, b: [k][n] per batch. */
 int isdf_gemm_hn_herm(void* handle, const void* a, long lda, long strideA, const void* b, long ldb, long strideB,

@@ -810,10 +810,11 @@ extern "C" int isdf_qrcp(void* hv, void* a, int n, int batch, void* vt, void* ta
   cudaStream_t st = (cudaStream_t)stream;
   ISDF_CHECK_ARG(h, a && vt && tau && piv && pos, "null pointer");
   ISDF_CHECK_ARG(h, n >= 1 && batch >= 1 && batch <= 65535, "shape");
-  // Large matrices: 16-CTA clusters when the batch leaves SMs idle otherwise (one 16-cluster per GPC: 8 at a time),
-  // 8-CTA clusters (16 at a time) when there are more matrices than that -- measured on B200 at n = 3120:
-  // 5 matrices 336 ms vs 498 ms, 36 matrices 2031 ms vs 1687 ms.
-  int cs = (n >= 1024 && batch <= 8) ? 16 : 8;
+  // 16-CTA clusters (9 resident at a time) up to 18 matrices, 8-CTA clusters (18 at a time) beyond -- measured on B200
+  // (tools/qrcp_cs_sweep.sh), 16 vs 8: n = 3120: 5 matrices 336 vs 552 ms, 18 matrices 1030 vs 1145 ms (two waves of 9
+  // beat one wave of 18), 36 matrices 2029 vs 1782 ms; one matrix of 1000: 25.6 vs 40.7 ms, of 1622: 60.7 vs 98.9 ms;
+  // 14 matrices of 520: 19.0 vs 12.6 ms.  The factorisation is bit-identical for every cluster size.
+  int cs = (n >= 768 && batch <= 18) ? 16 : 8;
   if (n < 64) cs = 1; else if (n < 256) cs = 2;
   if (const char* e = getenv("ISDF_QR_CS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) cs = v; }   // tuning
   ISDF_CUDA(h, cudaFuncSetAttribute(qrcp_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

@@ -14,7 +14,11 @@ the k2gamma supercell) and taken to k space with e^{-ik.R}; with Bloch AOs phi_k
 transformation", stub :246) the ERIs of the supercell AOs -- pinned by `tests/test_oracle_cpu.py::
 test_trans_2e_default_is_the_supercell_eri` against explicit supercell pair densities.
 
-Host-side consumer of `_x` / `_wq` (numpy), like the reference's own J/K; O(nk nip nemb^2 + nk nip^2 nemb^2) work.
+Two routes, same contraction: a host numpy statement (any object with numpy `_x` / `_wq`), and -- when `df_obj` is a
+built ISDF object, i.e. holds `_x_dev` / `_wq_dev` and the kernel handle -- the same five steps on the device through
+the library's own GEMM kernels (`isdf_gemm_nn/hn/tn`): Z_k = X_k C_k, the k-pair sums as nip small batched products,
+W_q applied to all q in one batched call, and the sum over q folded into the contraction length of the last product.
+O(nk nip nemb^2 + nk nip^2 nemb^2) work.
 """
 import numpy
 
@@ -39,8 +43,39 @@ def _add_spin_dim(c, spin):
     return numpy.concatenate([c] * spin, axis=0)
 
 
+def _contract_device(ops, x_dev, wq_dev, C_ao_emb, kmesh):
+    """eri[n][p,r,t,u] on the device; x_dev [nk,nip,nao], wq_dev [nk,nip,nip] (torch, complex128), C_ao_emb numpy
+    [spin,nk,nao,nemb].  Same pairing conventions as the host statement below (rho: k -> k+q, sig: k -> k-q)."""
+    import torch
+    c128 = torch.complex128
+    dev = x_dev.device
+    spin, nk, nao, nemb = C_ao_emb.shape
+    nip = x_dev.shape[1]
+    idx, inv = _kmesh_index_table(kmesh)
+    cdev = torch.from_numpy(numpy.ascontiguousarray(C_ao_emb)).to(dev)
+    z = [ops.gemm_nn(x_dev.contiguous(), cdev[s].contiguous()) for s in range(spin)]          # Z[s][k] = X_k C_k  [nip, nemb]
+    rho = torch.empty((spin, nk, nip, nemb, nemb), dtype=c128, device=dev)
+    sig = torch.empty_like(rho)
+    for q in range(nk):
+        kp = torch.as_tensor([inv[tuple(numpy.mod(idx[k] + idx[q], kmesh))] for k in range(nk)], device=dev)
+        km = torch.as_tensor([inv[tuple(numpy.mod(idx[k] - idx[q], kmesh))] for k in range(nk)], device=dev)
+        for s in range(spin):
+            a = z[s].permute(1, 0, 2)                                   # [I][k][p]: one nemb x nemb product per point I
+            ops.gemm_hn_strided(a, z[s].index_select(0, kp).permute(1, 0, 2), rho[s, q])   # sum_k conj(Z_k[I,p]) Z_{k+q}[I,r]
+            ops.gemm_hn_strided(a, z[s].index_select(0, km).permute(1, 0, 2), sig[s, q])
+    pairs = [(0, 0)] if spin == 1 else [(0, 0), (1, 1), (0, 1)]
+    n2 = nemb * nemb
+    eri = torch.empty((len(pairs), n2, n2), dtype=c128, device=dev)
+    half = torch.empty((n2, nk * nip), dtype=c128, device=dev)          # [p r][q, J]: the q sum becomes part of K
+    for n, (s1, s2) in enumerate(pairs):
+        r1 = rho[s1].reshape(nk, nip, n2)
+        ops.gemm_tn_strided(r1, wq_dev, half.view(n2, nk, nip).permute(1, 0, 2))           # half[q] = rho_q^T W_q
+        ops.gemm_nn_strided(half[None], sig[s2].reshape(1, nk * nip, n2), eri[n][None])
+    return eri.reshape(len(pairs), nemb, nemb, nemb, nemb).cpu().numpy()
+
+
 def trans_2e(df_obj, C_ao_lo=None, C_lo_eo=None, unit_eri=False, symmetry=1, t_reversal_symm=True, max_memory=None,
-             kscaled_center=None, kconserv_tol=KPT_DIFF_TOL, fname=None):
+             kscaled_center=None, kconserv_tol=KPT_DIFF_TOL, fname=None, on_device=None):
     """Signature of the stub at fftisdf.py:231-234.
 
     C_ao_lo [nk, nao, nlo] or [spin, nk, nao, nlo] (k space; default identity); C_lo_eo [ncell, nlo, nemb] or
@@ -51,11 +86,16 @@ def trans_2e(df_obj, C_ao_lo=None, C_lo_eo=None, unit_eri=False, symmetry=1, t_r
     if kscaled_center is not None:
         raise NotImplementedError("shifted k-meshes: the ISDF build assumes the Gamma-centred mesh (fftisdf.py:322)")
     assert symmetry in (1, 4)
-    xk = numpy.asarray(df_obj._x)
-    wq = numpy.asarray(df_obj._wq)
+    if on_device is None:   # a built ISDF object keeps its results on the GPU
+        on_device = getattr(df_obj, "_wq_dev", None) is not None and getattr(df_obj, "_ops", None) is not None
     kmesh = [int(n) for n in df_obj.kmesh]
+    if on_device:
+        xk, wq = df_obj._x_dev, df_obj._wq_dev
+    else:
+        xk = numpy.asarray(df_obj._x)
+        wq = numpy.asarray(df_obj._wq)
     nkpts, nip, nao = xk.shape
-    assert nkpts == int(numpy.prod(kmesh)) and wq.shape == (nkpts, nip, nip)          # :282-285
+    assert nkpts == int(numpy.prod(kmesh)) and tuple(wq.shape) == (nkpts, nip, nip)   # :282-285
 
     if C_ao_lo is None:                                                               # :246-250
         C_ao_lo = numpy.asarray([numpy.eye(nao) for _ in range(nkpts)], dtype=numpy.complex128)
@@ -86,6 +126,10 @@ def trans_2e(df_obj, C_ao_lo=None, C_lo_eo=None, unit_eri=False, symmetry=1, t_r
     spin, _, _, nemb = C_ao_emb.shape                                                 # :278-279
     assert C_ao_emb.shape == (spin, nkpts, nao, nemb) and spin in (1, 2)
 
+    if on_device:
+        eri = _contract_device(df_obj._ops, xk, wq, C_ao_emb, kmesh)
+        return _finish(eri, nemb, symmetry, t_reversal_symm, fname)
+
     # xmo[s, k] = C_ao_emb[s, k]^T X_k^T   [nemb, nip]                                  :287-289
     xmo = numpy.einsum("skan,kIa->sknI", C_ao_emb, xk)
 
@@ -110,6 +154,10 @@ def trans_2e(df_obj, C_ao_lo=None, C_lo_eo=None, unit_eri=False, symmetry=1, t_r
             half = numpy.einsum("Ipr,IJ->prJ", rho[s1, q], wq[q])
             eri[n] += numpy.einsum("prJ,Jtu->prtu", half, sig[s2, q])
 
+    return _finish(eri, nemb, symmetry, t_reversal_symm, fname)
+
+
+def _finish(eri, nemb, symmetry, t_reversal_symm, fname):
     if symmetry == 4:
         # real orbitals in a time-reversal-symmetric set: (pr|tu) is real and symmetric within each pair
         scale = max(numpy.abs(eri).max(), 1e-300)

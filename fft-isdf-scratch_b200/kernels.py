@@ -329,6 +329,17 @@ class IsdfOps:
         self.launches += 1
         return out
 
+    def gemm_tn_strided(self, a, b, out):
+        """out[z] = a[z]^T @ b[z] (no conjugation) into a strided view: a [batch,k,m], b [batch,k,n], out [batch,m,n]."""
+        assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
+        batch, k, m = a.shape
+        n = b.shape[2]
+        self.handle.check(self.lib.isdf_gemm_tn(self.h, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1),
+                                                b.stride(0), _ptr(out), out.stride(1), out.stride(0), m, n, k, batch,
+                                                _stream()), "isdf_gemm_tn")
+        self.launches += 1
+        return out
+
     def gemm_hn_strided(self, a, b, out):
         """out[z] = a[z]^H @ b[z] into a strided view: a [batch,k,m], b [batch,k,n], out [batch,m,n] (unit last stride)."""
         assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1

@@ -440,3 +440,28 @@ def test_kmesh_metric_equals_supercell_pair_gram():
         gram = phi0 @ sup.eval_ao_kpts(pts + r, gam)[0].real.T
         ref = nk * gram ** 2
         assert np.abs(x4_s[ir].real - ref).max() < 1e-12 * scale, ir
+
+
+@pytest.mark.parametrize("name", ["k231_odd", "k222_sp"])
+def test_trans_2e_device_route_equals_host_statement(name):
+    """trans_2e (the reference's stub fftisdf.py:230-294): the device contraction through the
+    library's GEMM kernels == the host numpy statement (itself pinned against the brute-force quadruple sum and the
+    explicit supercell ERIs in tests/test_oracle_cpu.py), for general two-spin orbitals, unit_eri and symmetry = 4."""
+    from fft_isdf_scratch_b200 import eri_transform as E
+    g, df = run_golden(name)
+    nk, nip, nao = df._x.shape
+    assert df._wq_dev is not None
+    rng = np.random.default_rng(5)
+    nlo, nemb = 5, 3
+    c_ao_lo = rng.standard_normal((2, nk, nao, nlo)) + 1j * rng.standard_normal((2, nk, nao, nlo))
+    c_lo_eo = rng.standard_normal((1, nk, nlo, nemb))
+    dev = E.trans_2e(df, C_ao_lo=c_ao_lo, C_lo_eo=c_lo_eo)                       # auto: on the device
+    host = E.trans_2e(df, C_ao_lo=c_ao_lo, C_lo_eo=c_lo_eo, on_device=False)
+    assert dev.shape == host.shape == (3, nemb, nemb, nemb, nemb)
+    tol = 1e-10        # normwise bound of the 3M products over a W_q spanning many decades (k231_odd: < 1e-12)
+    assert rel(dev, host) < tol
+    dev_u = E.trans_2e(df, C_ao_lo=c_ao_lo[0], unit_eri=True)
+    assert rel(dev_u, E.trans_2e(df, C_ao_lo=c_ao_lo[0], unit_eri=True, on_device=False)) < tol
+    if name == "k222_sp":                                                        # default orbitals: supercell AOs, real ERIs
+        p4 = E.trans_2e(df, symmetry=4)
+        assert p4.dtype == np.float64 and rel(p4, E.trans_2e(df, symmetry=4, on_device=False)) < tol

@@ -659,7 +659,8 @@ class InterpolativeSeparableDensityFitting(_Base):
             kpts = self.kpts
         kpts = numpy.asarray(kpts)
         assert getattr(cell, "dimension", 3) == 3
-        if _HAVE_PYSCF and hasattr(self, "_numint") and not hasattr(cell, "_images"):
+        have_tables = getattr(self, "_ao_tables_dev", None) is not None or getattr(self, "_ao_tables", None) is not None
+        if _HAVE_PYSCF and hasattr(self, "_numint") and not hasattr(cell, "_images") and not have_tables:
             if grids.non0tab is None:
                 grids.build(with_non0tab=True)
             p1 = 0

@@ -820,12 +820,18 @@ extern "C" int isdf_qrcp(void* hv, void* a, int n, int batch, void* vt, void* ta
   ISDF_CUDA(h, cudaFuncSetAttribute(qrcp_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   int ncc = 0, nb = 0, nvb = 0;
   size_t smem = 0;
+  const long budget = (long)h->max_smem_optin - 34 * 1024;      // static shared memory of the kernel
+  // The panel width fixes the order of the deferred updates, i.e. the rounding of R: it must not follow the cluster
+  // size (which follows the number of matrices per GPU), or an N-GPU build would cut the eps-plateau of |R_kk| at other
+  // ranks than the single-GPU build.  It is therefore the width that fits the 8-CTA geometry, for 16-CTA clusters too
+  // (n = 3120: 16, although 32 would fit 16 CTAs).
+  int nb_ref = QR_NB_MAX;
+  while (nb_ref > 4 && (long)qr_smem_bytes(n, (n + 7) / 8, nb_ref, nullptr) > budget) nb_ref /= 2;
   for (;; cs /= 2) {
     ncc = (n + cs - 1) / cs;
-    const long budget = (long)h->max_smem_optin - 34 * 1024;    // static shared memory of the kernel
     bool ok = ncc <= QR_THREADS * QR_NCOLT;
     if (ok) {
-      nb = QR_NB_MAX;
+      nb = nb_ref;
       while (nb >= 4 && (long)qr_smem_bytes(n, ncc, nb, &nvb) > budget) nb /= 2;
       ok = nb >= 4;
     }

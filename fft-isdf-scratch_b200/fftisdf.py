@@ -446,8 +446,7 @@ def build(df_obj):
                 cache.clear()
                 cache[key] = sharding.PeerBuffer((n_own, world, nipP, nipP), dev, comm)
             slabs = cache[key]
-            dst = [slabs.ptrs[s % world] + 16 * ((s // world) * world + rank) * nipP * nipP for s in range(nq)]
-            assert mine == list(range(rank, nq, world))          # slot s lives on rank s % world at index s // world
+            dst = sharding.slab_destinations(nq, world, rank, nipP * nipP, base_ptrs=slabs.ptrs)
             dst_d = torch.tensor(dst, dtype=torch.int64, device=dev)
             slabs.barrier()                                      # the owners are done with the previous build's slabs
             with ops.timed("herk"):

@@ -44,6 +44,18 @@ def slot_shard(nslot, world, rank):
     return list(range(rank, nslot, world))
 
 
+def slab_destinations(nslot, world, rank, slab_elems, base_ptrs=None, itemsize=16):
+    """Fused reduce-scatter of the partial W~ (isdf_herk_to_peers): q-slot s is owned by rank s % world (slot_shard) and
+    is that rank's local slot s // world; rank `rank` writes its partial product into slab `rank` of that local slot.
+    Returns (owner[s], offset[s]) with the offset in ELEMENTS inside the owner's [n_own][world][slab_elems] buffer, or
+    the absolute byte addresses when the ranks' base pointers are given."""
+    owner = [s % world for s in range(nslot)]
+    off = [((s // world) * world + rank) * slab_elems for s in range(nslot)]
+    if base_ptrs is None:
+        return owner, off
+    return [int(base_ptrs[o]) + itemsize * f for o, f in zip(owner, off)]
+
+
 def _a2a(out, inp, group):
     dist.all_to_all_single(torch.view_as_real(out), torch.view_as_real(inp), group=group)
 

@@ -22,9 +22,14 @@
  *                                       or isdf_ktransform_square (shared memory; axes <= 8)
  *   build rhs       fftisdf.py:72-87    isdf_gram_conjb -> isdf_ktransform_square_rows, per grid block, rows written
  *                                       straight into pivot order
- *   fit theta       fftisdf.py:108      isdf_pchol -> isdf_trsm_prepare -> isdf_trsm_sweeps
- *   coulomb kernel  fftisdf.py:96-122   isdf_phase_table + isdf_coulomb_weights -> isdf_dft3d_dmma (axes <= 48; _p2p
- *                                       across GPUs) or isdf_fft3d_batched -> isdf_herk_scatter -> isdf_conj_copy
+ *   fit theta       fftisdf.py:108      zgelsy on the device (default): isdf_qrcp -> isdf_gelsy_rank -> the dense operators
+ *                                       G = U^-H D^-1 Q1^H and E^H per q (isdf_gelsy_extract / _rhat / _q1h_finish,
+ *                                       isdf_chol_nopivot, isdf_herk_scatter, isdf_gemm_*) -> isdf_gemm_nn (Theta~ = G Y^T,
+ *                                       per grid block);  fit = "cholesky": isdf_pchol -> isdf_trsm_prepare -> isdf_trsm_sweeps
+ *   coulomb kernel  fftisdf.py:96-122   isdf_phase_table + isdf_coulomb_weights -> isdf_fft3d_reg (instantiated lengths; _p2p
+ *                                       across GPUs), isdf_dft3d_dmma (other meshes with axes <= 48; _p2p) or
+ *                                       isdf_fft3d_batched -> isdf_herk_scatter (isdf_herk_to_peers + isdf_sum_slabs_herm
+ *                                       across GPUs) -> isdf_gemm_nn + isdf_gemm_hn_herm (W = E W~ E^H) -> isdf_conj_copy
  *   J / K           fftisdf.py:133-228  isdf_gemm_hn, isdf_rowdot_conj_sum, isdf_scale_rows, isdf_ktransform_rows_ex
  */
 #ifndef ISDF_B200_H

@@ -84,3 +84,24 @@ def test_col_shard_covers_grid():
                 assert hi - lo <= c
                 seen += list(range(lo, hi))
             assert seen == list(range(ng))
+
+
+def test_slab_destinations_cover_every_owner_slot_once():
+    """Fused reduce-scatter of W~: the (owner, offset) every rank writes q-slot s to must be the owner's local index of
+    that slot (slot_shard) and slab = writer rank -- all world x nslot slabs distinct and inside the owner's buffer."""
+    from fft_isdf_scratch_b200 import sharding
+    for nslot, world in [(36, 8), (14, 2), (3, 4), (1, 2), (36, 1)]:
+        slab = 7
+        n_own = -(-nslot // world)
+        seen = set()
+        for rank in range(world):
+            owner, off = sharding.slab_destinations(nslot, world, rank, slab)
+            for s in range(nslot):
+                mine = sharding.slot_shard(nslot, world, owner[s])
+                assert s in mine
+                assert off[s] == (mine.index(s) * world + rank) * slab
+                assert 0 <= off[s] and off[s] + slab <= n_own * world * slab
+                seen.add((owner[s], off[s]))
+            ptrs = sharding.slab_destinations(nslot, world, rank, slab, base_ptrs=[1000 * (r + 1) for r in range(world)])
+            assert ptrs == [1000 * (o + 1) + 16 * f for o, f in zip(owner, off)]
+        assert len(seen) == nslot * world

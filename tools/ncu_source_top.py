@@ -1,12 +1,12 @@
-"""Top source lines of an .ncu-rep by warp-stall samples:  python tools/ncu_source_top.py prof.ncu-rep out.csv [n]"""
+"""Top SASS instructions of an .ncu-rep (captured with --set full or --section SourceCounters) by warp-stall samples:
+python tools/ncu_source_top.py prof.ncu-rep out.csv [n]"""
 import csv
 import subprocess
 import sys
 
 rep, out = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 60
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True,
-                     text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = [r for r in csv.reader(raw.splitlines()) if r]
 hdr = None
 data = []

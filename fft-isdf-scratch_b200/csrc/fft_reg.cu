@@ -16,12 +16,16 @@
 namespace isdf {
 namespace fftreg {
 
-RegPlanSlice fft_reg_slice0();
-RegPlanSlice fft_reg_slice1();
-RegPlanSlice fft_reg_slice2();
+#define ISDF_FFT_PART(k) RegPlanSlice fft_reg_slice##k();
+#include "fft_reg_parts.inc"
+#undef ISDF_FFT_PART
 
 static const RegPlan* find_plan(int n) {
-  const RegPlanSlice sl[3] = {fft_reg_slice0(), fft_reg_slice1(), fft_reg_slice2()};
+  const RegPlanSlice sl[] = {
+#define ISDF_FFT_PART(k) fft_reg_slice##k(),
+#include "fft_reg_parts.inc"
+#undef ISDF_FFT_PART
+  };
   for (const RegPlanSlice& s : sl)
     for (int i = 0; i < s.count; ++i)
       if (s.plans[i].n == n) return &s.plans[i];

@@ -110,6 +110,9 @@ int main() {
 #include "fft_reg_sizes_p0.inc"
 #include "fft_reg_sizes_p1.inc"
 #include "fft_reg_sizes_p2.inc"
+#include "fft_reg_sizes_p3.inc"
+#include "fft_reg_sizes_p4.inc"
+#include "fft_reg_sizes_p5.inc"
   };
   (void)dummy;
   printf("worst %.2e\n", worst);
